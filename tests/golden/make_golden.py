@@ -1,0 +1,269 @@
+"""Generate the golden fixtures in tests/golden/ by RUNNING THE REFERENCE'S OWN PYTHON CODE.
+
+Run in the build container only (``/root/reference`` must exist; it does not on the GPU box):
+
+    python tests/golden/make_golden.py
+
+What runs unmodified from /root/reference (imported / compiled from the files where they lie,
+nothing is copied into this repo):
+  * environment/maze_env.py  MazeEnv (_state_fp, _edge_fp, collision_check_count)  -- real NumPy code
+  * model.py                 EncoderProcessDecoder.forward with shipped weights
+  * model_smoother.py        ModelSmoother.forward with shipped weights
+  * eval_gnn.py              create_data, explore  (function bodies compiled out of the file via ast,
+                             because importing the module pulls pybullet/matplotlib)
+  * smoother.py              model_smooth, obs_data, proposed_path_smootherv2 (same way)
+Third-party primitives that are not installable here (torch_geometric / torch_cluster /
+torch_sparse / torch_scatter) are replaced by tests/golden/_pyg_stubs.py, which restates their
+published semantics -- so these vectors pin our oracle + kernels to the reference's python, and
+are "unpinned" only at the PyG-primitive boundary.
+
+Also copies the shipped weight files the parity tests and bench need into tests/golden/weights/
+(binary fixtures, not source).
+"""
+import ast
+import os
+import shutil
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get("GNNMP_REFERENCE", "/root/reference")
+sys.path.insert(0, HERE)
+import _pyg_stubs  # noqa: E402
+
+_pyg_stubs.install()
+
+
+def load_ref_maze_env():
+    """Import reference environment/maze_env.py without environment/__init__.py (which needs pybullet)."""
+    import importlib.util
+    pkg = types.ModuleType("environment")
+    pkg.__path__ = [os.path.join(REF, "environment")]
+    sys.modules["environment"] = pkg
+    for name in ("env_config", "maze_env", "timer"):
+        spec = importlib.util.spec_from_file_location("environment." + name,
+                                                      os.path.join(REF, "environment", name + ".py"))
+        m = importlib.util.module_from_spec(spec)
+        sys.modules["environment." + name] = m
+        spec.loader.exec_module(m)
+        setattr(pkg, name, m)
+    return sys.modules["environment.maze_env"].MazeEnv
+
+
+def ref_functions(pyfile, names, namespace):
+    """Compile selected top-level functions/classes out of a reference file into ``namespace``."""
+    src = open(os.path.join(REF, pyfile)).read()
+    tree = ast.parse(src)
+    keep = [n for n in tree.body if isinstance(n, (ast.FunctionDef, ast.ClassDef)) and n.name in names]
+    assert len(keep) == len(names), (pyfile, names)
+    mod = ast.Module(body=keep, type_ignores=[])
+    exec(compile(mod, os.path.join(REF, pyfile), "exec"), namespace)
+    return namespace
+
+
+def sym_knn_edges(v, k):
+    ei = _pyg_stubs.knn_graph(v, k, loop=True)
+    ei = torch.cat([ei, ei.flip(0)], 1)
+    return _pyg_stubs.coalesce(ei, None, len(v), len(v))[0]
+
+
+def main():
+    os.chdir(REF)  # MazeEnv opens 'maze_files/...' relative to cwd
+    sys.path.insert(0, REF)
+    MazeEnv = load_ref_maze_env()
+    import model as ref_model
+    import model_smoother as ref_model_smoother
+
+    # ---------------------------------------------------------------- weights (binary fixtures)
+    wdir = os.path.join(HERE, "weights")
+    os.makedirs(wdir, exist_ok=True)
+    for w in ("weights_maze.pt", "weights_kuka.pt", "kuka_14.pt", "smooth_2d_attv3.pt", "smooth_7d_attv3.pt"):
+        shutil.copyfile(os.path.join(REF, "data/weights", w), os.path.join(wdir, w))
+
+    # ---------------------------------------------------------------- maze problems subset
+    env = MazeEnv(dim=2)
+    prob_ids = np.array([0, 1, 2, 3, 7, 100, 2000, 2001, 2500, 2999])
+    np.savez_compressed(os.path.join(HERE, "maze_problems.npz"),
+                        ids=prob_ids, maps=env.maps[prob_ids].astype(np.uint8),
+                        init_states=env.init_states[prob_ids], goal_states=env.goal_states[prob_ids])
+    # a larger map pool (maps only, uint8) for the synthetic bench / full-size property tests
+    np.savez_compressed(os.path.join(HERE, "maze_maps_256.npz"), maps=env.maps[:256].astype(np.uint8))
+
+    # ---------------------------------------------------------------- maze collision golden
+    rng = np.random.default_rng(20211206)
+    out = {}
+    for dt in (np.float32, np.float64):
+        S, SP, SF, SC = [], [], [], []
+        A, B, EP, EF, EC, EK = [], [], [], [], [], []
+        for pi, pid in enumerate(prob_ids):
+            env.init_new_problem(int(pid))
+            # states: uniform in [-1.1,1.1] (some out of range), grid-boundary values, exact +-1
+            st = rng.uniform(-1.1, 1.1, (300, 2))
+            edges_of_grid = (np.arange(0, 16) * 2.0 / 15 - 1.0)
+            bd = np.stack([rng.choice(edges_of_grid, 60), rng.uniform(-1, 1, 60)], 1)
+            bd2 = bd[:, ::-1] + rng.choice([0, 1e-7, -1e-7, 1e-16], (60, 1))
+            st = np.concatenate([st, bd, bd2, [[1, 1], [-1, -1], [1, -1], [0, 0], [1.0000001, 0]]]).astype(dt)
+            for s in st:
+                c0 = env.collision_check_count
+                f = bool(env._state_fp(s))
+                S.append(s); SP.append(pi); SF.append(f); SC.append(env.collision_check_count - c0)
+            # edges: pairs among free samples (kNN-like short ones and long ones) + random pairs
+            free = np.array(env.sample_n_points(150)).astype(dt)
+            allp = rng.uniform(-1.05, 1.05, (150, 2)).astype(dt)
+            pairs = []
+            for _ in range(500):
+                i, j = rng.integers(0, len(free), 2)
+                pairs.append((free[i], free[j]))
+            d = ((free[:, None, :] - free[None, :, :]) ** 2).sum(-1)
+            nn = np.argsort(d, axis=1)[:, :5]
+            for i in range(len(free)):
+                for j in nn[i]:
+                    pairs.append((free[i], free[j]))
+            for _ in range(250):
+                i, j = rng.integers(0, len(allp), 2)
+                pairs.append((allp[i], free[j % len(free)]))
+                pairs.append((free[i % len(free)], allp[j]))
+            for a, b in pairs:
+                c0 = env.collision_check_count
+                f = bool(env._edge_fp(a, b))
+                A.append(a); B.append(b); EP.append(pi); EF.append(f)
+                EC.append(env.collision_check_count - c0); EK.append(env.k)
+        tag = "f32" if dt == np.float32 else "f64"
+        out.update({
+            "states_" + tag: np.array(S, dt), "state_problem_" + tag: np.array(SP, np.int32),
+            "state_free_" + tag: np.array(SF, np.uint8), "state_counted_" + tag: np.array(SC, np.uint8),
+            "edge_a_" + tag: np.array(A, dt), "edge_b_" + tag: np.array(B, dt),
+            "edge_problem_" + tag: np.array(EP, np.int32), "edge_free_" + tag: np.array(EF, np.uint8),
+            "edge_checks_" + tag: np.array(EC, np.int32), "edge_k_" + tag: np.array(EK, np.int32),
+        })
+    np.savez_compressed(os.path.join(HERE, "maze_collision.npz"), **out)
+    print("maze_collision:", {k: v.shape for k, v in out.items() if k.startswith("edge_free")},
+          "free frac", out["edge_free_f32"].mean())
+
+    # ---------------------------------------------------------------- create_data golden (eval_gnn.py:150-165)
+    ns = dict(torch=torch, np=np, Data=_pyg_stubs.Data, knn_graph=_pyg_stubs.knn_graph, coalesce=_pyg_stubs.coalesce)
+    ref_functions("eval_gnn.py", ["create_data"], ns)
+    cd = {}
+    for tag, (c, nf, ncol, k) in {"maze2": (2, 102, 60, 10), "kuka7": (7, 90, 90, 12), "kuka14": (14, 150, 40, 8),
+                                  "dup": (2, 40, 10, 10)}.items():
+        free = [rng.uniform(-1, 1, c) for _ in range(nf)]
+        collided = [rng.uniform(-1, 1, c) for _ in range(ncol)]
+        if tag == "dup":  # duplicated points => exact distance ties
+            free[5] = free[4].copy(); collided[3] = free[9].copy()
+        fake_env = types.SimpleNamespace(goal_state=free[1])
+        d = ns["create_data"](free, collided, fake_env, k)
+        cd.update({tag + "_free": np.array(free), tag + "_collided": np.array(collided), tag + "_k": np.array(k),
+                   tag + "_v": d.v.numpy(), tag + "_labels": d.labels.numpy(),
+                   tag + "_edge_index": d.edge_index.numpy(), tag + "_goal": d.goal.numpy()})
+        print("create_data", tag, d.edge_index.shape)
+    np.savez_compressed(os.path.join(HERE, "create_data.npz"), **cd)
+
+    # ---------------------------------------------------------------- explorer golden (model.py:115-150)
+    ex = {}
+    cfgs = {
+        "maze2": dict(w="weights_maze.pt", c=2, e=32, s=2, ws=2, n=200, k=10, lo=-1.0, hi=1.0),
+        "kuka7": dict(w="weights_kuka.pt", c=7, e=64, s=6, ws=3, n=150, k=8, lo=-2.9, hi=2.9),
+        "kuka14": dict(w="kuka_14.pt", c=14, e=32, s=6, ws=3, n=160, k=8, lo=-2.9, hi=2.9),
+    }
+    for tag, cf in cfgs.items():
+        m = ref_model.EncoderProcessDecoder(workspace_size=cf["ws"], config_size=cf["c"], embed_size=cf["e"],
+                                            obs_size=cf["s"])
+        m.load_state_dict(torch.load(os.path.join(REF, "data/weights", cf["w"]), map_location="cpu"))
+        m.eval()
+        v = torch.from_numpy(rng.uniform(cf["lo"], cf["hi"], (cf["n"], cf["c"])).astype(np.float32))
+        ei = sym_knn_edges(v, cf["k"])
+        if tag == "maze2":
+            env.init_new_problem(2000)
+            obs = torch.FloatTensor(env.obstacles)                     # [O,2]
+        else:
+            nb = 5
+            obs = torch.from_numpy(np.concatenate([rng.uniform(0.1, 0.3, (nb, 1, 3)),
+                                                   rng.uniform(-0.8, 0.8, (nb, 1, 3))], 1).astype(np.float32))  # [O,2,3]
+        for loop in (1, 5):
+            with torch.no_grad():
+                dense = m(goal=v[1], loop=loop, v=v, obstacles=obs, free=None, collided=None, edge_index=ei,
+                          labels=None)
+            ex["%s_logits_loop%d" % (tag, loop)] = dense[ei[1], ei[0]].numpy()
+            assert int((dense != 0).sum()) <= ei.shape[1]
+        m.use_obstacles = False
+        with torch.no_grad():
+            dense = m(goal=v[1], loop=5, v=v, obstacles=obs, free=None, collided=None, edge_index=ei)
+        ex[tag + "_logits_noobs"] = dense[ei[1], ei[0]].numpy()
+        ex.update({tag + "_v": v.numpy(), tag + "_edge_index": ei.numpy(), tag + "_obstacles": obs.numpy(),
+                   tag + "_goal": v[1].numpy()})
+        print("explorer", tag, ei.shape, float(ex[tag + "_logits_loop5"].mean()), float(ex[tag + "_logits_loop5"].std()))
+    np.savez_compressed(os.path.join(HERE, "explorer.npz"), **ex)
+
+    # ---------------------------------------------------------------- smoother golden (model_smoother.py:104-142)
+    sm = {}
+    for tag, (w, c, p, nf, ncol) in {"2d": ("smooth_2d_attv3.pt", 2, 9, 70, 40), "7d": ("smooth_7d_attv3.pt", 7, 14, 60, 50),
+                                     "2d_short": ("smooth_2d_attv3.pt", 2, 3, 12, 1)}.items():
+        ms = ref_model_smoother.ModelSmoother(workspace_size=3, config_size=c, embed_size=128, obs_size=6)
+        ms.load_state_dict(torch.load(os.path.join(REF, "data/weights", w), map_location="cpu"))
+        ms.eval()
+        lo, hi = (-1, 1) if c == 2 else (-2.9, 2.9)
+        path = torch.from_numpy(np.cumsum(rng.uniform(-0.1, 0.15, (p, c)), 0).astype(np.float32)).clamp(lo, hi)
+        free = torch.from_numpy(rng.uniform(lo, hi, (nf, c)).astype(np.float32))
+        coll = torch.from_numpy(rng.uniform(lo, hi, (ncol, c)).astype(np.float32))
+        e = torch.cat((torch.arange(1, p).reshape(1, -1), torch.arange(0, p - 1).reshape(1, -1)), 0)
+        e = torch.cat((e, e.flip(0)), -1)
+        e, _ = _pyg_stubs.add_self_loops(e, num_nodes=p)
+        for loop in (1, 3):
+            with torch.no_grad():
+                newp = ms(path=path.clone(), free=free, collided=coll, obstacles=None, edge_index=e, loop=loop)
+            sm["%s_out_loop%d" % (tag, loop)] = newp.numpy()
+        sm.update({tag + "_path": path.numpy(), tag + "_free": free.numpy(), tag + "_collided": coll.numpy(),
+                   tag + "_edge_index": e.numpy()})
+        print("smoother", tag, newp.shape)
+    np.savez_compressed(os.path.join(HERE, "smoother.npz"), **sm)
+
+    # ---------------------------------------------------------------- end-to-end explore() golden: BASELINE config C1
+    # reference eval_gnn.explore(batch=100, t_max=100, k=10, smoother='none') on real maze problems
+    # (main.ipynb cell 8 / BASELINE.json configs[0]) with the reference MazeEnv and reference model.
+    import time as _time
+    ns = dict(torch=torch, np=np, Data=_pyg_stubs.Data, knn_graph=_pyg_stubs.knn_graph, coalesce=_pyg_stubs.coalesce,
+              time=_time.time, device=torch.device("cpu"), loop=5)
+    ns["DotDict"] = type("DotDict", (dict,), dict(__getattr__=dict.get, __setattr__=dict.__setitem__))
+    ref_functions("eval_gnn.py", ["create_data", "explore", "obs_data", "to_np", "path_cost"], ns)
+    m = ref_model.EncoderProcessDecoder(workspace_size=2, config_size=2, embed_size=32, obs_size=2)
+    m.load_state_dict(torch.load(os.path.join(REF, "data/weights/weights_maze.pt"), map_location="cpu"))
+    m.eval()
+
+    # eval_gnn.py:202 `policy[np.array(explored_edges).reshape(2, -1)] = 0` relies on the torch<=1.x rule
+    # that a short non-tuple SEQUENCE of sequences (here a (2,M) ndarray) is treated as a TUPLE of index
+    # arrays (policy[rows, cols]); torch 2.x indexes ROWS instead, which zeroes row 0 and the search never
+    # starts (success 0/6 here, vs 1000/1000 in the author's main.ipynb).  Restore the author-era rule
+    # without touching the reference code: the model wrapper returns a Tensor subclass whose
+    # __setitem__ re-applies the legacy interpretation.
+    class LegacyIndexTensor(torch.Tensor):
+        def __setitem__(self, idx, val):
+            if isinstance(idx, np.ndarray) and idx.ndim == 2 and idx.shape[0] < 32:
+                idx = tuple(torch.from_numpy(r) for r in idx)
+            return super().__setitem__(idx, val)
+
+    ref_forward = m.forward
+
+    def legacy_forward(*a, **k):
+        return ref_forward(*a, **k).as_subclass(LegacyIndexTensor)
+    m.forward = legacy_forward
+    e2e = {}
+    ids = [2000, 2001, 2002, 2003, 2004, 2005]
+    for pid in ids:
+        np.random.seed(1234 + pid)
+        env.init_new_problem(pid)
+        r = ns["explore"](env, m, None, smooth=True, batch=100, t_max=100, k=10, smoother="none")
+        e2e["p%d_success" % pid] = np.array(r["success"])
+        e2e["p%d_c_explore" % pid] = np.array(r["c_explore"])
+        e2e["p%d_explored" % pid] = np.array(r["explored"])
+        e2e["p%d_path" % pid] = np.array(r["path"])
+        e2e["p%d_n_nodes" % pid] = np.array(len(r["data"].v))
+        print("explore", pid, r["success"], r["c_explore"], len(r["explored"]), len(r["data"].v))
+    e2e["ids"] = np.array(ids)
+    np.savez_compressed(os.path.join(HERE, "explore_c1.npz"), **e2e)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,77 @@
+// Opaque handle shared by the translation units of libgnnmp.so.
+#pragma once
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace gmp {
+
+// One attention Block of a map stream (model.py:204-218), device-packed.  All offsets are in floats
+// into the packed weight image; every matrix is stored K-major (Wt[k][n]) and is immediately
+// followed by the vectors its stage needs, so a stage is ONE contiguous global->shared copy.
+struct BlockW {
+  int Gt;    // [E][E]  scale * Wq^T Wk        (self score  s = x^T G x)
+  int Wvt;   // [E][E] | ln_g[E] | ln_b[E]      (value, attention.layer_norm)
+  int W1t;   // [E][E] | b1[E]                  (map_feed.w_1)
+  int W2t;   // [E][E] | b2[E] | ln_g | ln_b    (map_feed.w_2, map_feed.layer_norm)
+};
+struct ObsBlockW {
+  int Wkt;   // [E][E]                          key
+  int WqS;   // [E][E]  scale * Wq              (M_o = scale * Wq^T key_o)
+  int Wvt;   // [E][E]                          value
+  int W1t;   // [E][E] | b1                     (obs_feed.w_1)
+  int W2t;   // [E][E] | b2 | ln_g | ln_b       (obs_feed.w_2, obs_feed.layer_norm)
+};
+struct ExplorerW {
+  BlockW node_blk[3], edge_blk[3];
+  ObsBlockW obs_blk[2][3];           // [stream: 0 node, 1 edge]
+  int obs0[2], obs2[2];              // obs_{node,edge}_code.{0,2}: [Wt | b]
+  int nc0, nc2, nf0, nf2;            // node_code / node_free_code: [Wt | b]
+  int ef0, ef2, ec0, ec2;            // edge_free_code / edge_code: [Wt | b]
+  int enc_nc, enc_nf, enc_u3, enc_h; // encoder slices: We1t ; [We2t | b] ; We3*goal_encoder [E] ; We4t
+  int dec_nc, dec_h;                 // decoder slices: [Wd1t | b] ; Wd2t
+  int l0_ef, l0_ec;                  // lin_0.0 slices on edge_free / edge_code: W4t ; [W5t | b]
+  int l0_A, l0_B;                    // (W1+W2)^T ; (W3-W1)^T
+  int l0_2;                          // lin_0.2: [Wt | b]
+  int l1_x, l1_a;                    // lin_1 slices: Wxt ; [Wat | b]
+  int p0_ef, p0_G, p0_H;             // policy.0: [Wct | b] ; (Wa+Wb)^T ; (-Wb)^T
+  int p2;                            // policy.2: [Wt | b | policy.4 weight [E]]
+  int goal_enc;                      // [E]
+};
+
+struct ExplorerModel {
+  int c = 0, e = 0, s = 0;
+  bool ready = false;
+  std::map<std::string, std::vector<float>> tensors;  // reference state_dict (live entries)
+  ExplorerW w{};
+  float* d_weights = nullptr;
+  int64_t n_weights = 0;
+};
+
+struct SmootherW {
+  int nc0;   // node_code.0 with BatchNorm (eval) folded: [Wt (c+3 x E) | b]
+  int nc3;   // node_code.3: [Wt | b]
+  int l0_A, l0_B;  // lin_0.0 split: (W1+W2)^T ; [(W3-W1)^T | b]
+  int l0_2;  // [Wt | b]
+  int l1_0, l1_2;  // [Wt | b]
+  int sm;    // smooth_node: [Wt (E x CP) | b (CP)], CP = c rounded up to 4
+};
+
+struct SmootherModel {
+  int c = 0, e = 0;
+  bool ready = false;
+  std::map<std::string, std::vector<float>> tensors;
+  SmootherW w{};
+  float* d_weights = nullptr;
+  int64_t n_weights = 0;
+};
+
+}  // namespace gmp
+
+struct gmp_handle {
+  int device = 0;
+  gmp::ExplorerModel ex;
+  gmp::SmootherModel sm;
+};

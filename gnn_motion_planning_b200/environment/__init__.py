@@ -1,0 +1,4 @@
+"""Environment mirrors (reference ``environment/``): same duck-typed env protocol, collision checks on the GPU."""
+from .maze_env import MazeEnv  # noqa: F401
+
+strs = ['maze2', 'kuka7', 'snake7', 'kuka13', 'ur5', 'kuka14']

@@ -1,0 +1,128 @@
+/* gnnmp.h -- C ABI of libgnnmp.so: the B200 (sm_100a) implementation of the data-parallel hot
+ * path of rainorangelemon/gnn-motion-planning.
+ *
+ * The reference is pure Python and has no FFI; its seam for this path is a set of Python call
+ * sites.  Each entry point below names the reference interface it replaces
+ * (file:line, relative to the reference root).  The reference-side binding a maintainer would add
+ * is a ctypes stub -- see INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C, no torch types.  Pointers are DEVICE pointers unless the name ends in `_h`.
+ *   - the caller allocates every input, output and workspace buffer; nothing is retained after a
+ *     call returns except the weights owned by a handle.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Calls only enqueue
+ *     work; they do not synchronise unless stated.
+ *   - return value: 0 = OK, negative = GMP_E_*; gmp_last_error() gives the message (thread local).
+ *   - batches are PACKED: graph g owns nodes  node_ptr[g] .. node_ptr[g+1]  of `v`, edges
+ *     edge_ptr[g] .. edge_ptr[g+1] of `edge_index`, obstacle rows obs_ptr[g] .. obs_ptr[g+1].
+ *     The *_ptr offset arrays are HOST arrays (the caller knows its own sizes); node ids inside
+ *     edge_index are LOCAL to their graph (0 .. N_g-1), int64 like torch_geometric's edge_index:
+ *     row 0 = source j, row 1 = target i, stored as [2, E_total] (row stride = E_total).
+ *   - there is NO CPU fallback anywhere in this library.
+ */
+#ifndef GNNMP_H_
+#define GNNMP_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GMP_OK 0
+#define GMP_E_INVALID (-1)   /* bad argument / shape */
+#define GMP_E_CUDA (-2)      /* CUDA runtime error */
+#define GMP_E_STATE (-3)     /* handle not ready (weights missing) */
+#define GMP_E_UNSUPPORTED (-4)
+
+#define GMP_DTYPE_F32 0
+#define GMP_DTYPE_F64 1
+
+typedef struct gmp_handle gmp_handle;
+
+/* ---- library ------------------------------------------------------------------------------ */
+const char* gmp_last_error(void);
+const char* gmp_version(void);
+/* 1 if a CUDA device of compute capability 10.x is visible; never throws. */
+int gmp_device_ok(int device);
+
+gmp_handle* gmp_create(int device);
+void gmp_destroy(gmp_handle* h);
+
+/* ---- explorer: EncoderProcessDecoder (model.py:48-150) -------------------------------------- */
+/* Replaces nn.Module construction (model.py:49) : dims of the model this handle serves. */
+int gmp_explorer_init(gmp_handle* h, int config_size /*c*/, int embed_size /*e: 32 or 64*/, int obs_size /*s*/);
+/* Replaces load_state_dict (eval_gnn.py:101): hand over one reference state_dict tensor by its
+ * reference name (e.g. "process.lin_0.0.weight"), host fp32, row-major as torch stores it.
+ * Dead tensors of the reference dict are accepted and ignored. */
+int gmp_explorer_set_tensor(gmp_handle* h, const char* name, const float* data_h, int64_t numel);
+/* Validates that every live tensor arrived with the right size, builds the device-side packed
+ * (transposed / algebraically pre-combined) weight image. */
+int gmp_explorer_finalize(gmp_handle* h);
+
+/* Bytes of scratch gmp_explorer_forward needs for a batch of these totals. */
+int64_t gmp_explorer_workspace_bytes(const gmp_handle* h, int64_t n_graphs, int64_t n_nodes_total,
+                                     int64_t n_edges_total, int64_t n_obs_total);
+
+/* Replaces EncoderProcessDecoder.forward (model.py:115-150) for a packed batch of graphs.
+ *   v            [N_total, c] f32        node configurations               (model.py:115 `v`)
+ *   edge_index   [2, E_total] i64        local node ids                    (`edge_index`)
+ *   edge_row_stride  elements between row 0 and row 1 of edge_index (>= E_total; = E_total when contiguous)
+ *   goal         [B, c] f32                                                 (`goal`)
+ *   obstacles    [O_total, s] f32        obstacle tokens, already viewed [-1, s] (model.py:126)
+ *   node_ptr_h / edge_ptr_h / obs_ptr_h  [B+1] i32 host offset arrays
+ *   loop         message-passing rounds (eval_gnn.py:14: 5)
+ *   use_obstacles  model.use_obstacles (model.py:125)
+ *   edge_logits_out [E_total] f32        logit of edge e, aligned with edge_index   (the `policy` vector, model.py:145)
+ *   dense_out    nullable; sum_g N_g^2 f32, graph g at offset sum_{g'<g} N_g'^2, out[dst*N_g+src] = logit,
+ *                zero elsewhere                                             (model.py:148-150)
+ *   workspace    >= gmp_explorer_workspace_bytes(...)
+ */
+int gmp_explorer_forward(gmp_handle* h, int64_t n_graphs, const float* v, const int64_t* edge_index,
+                         int64_t edge_row_stride, const float* goal, const float* obstacles, const int32_t* node_ptr_h,
+                         const int32_t* edge_ptr_h, const int32_t* obs_ptr_h, int loop, int use_obstacles,
+                         float* edge_logits_out, float* dense_out, void* workspace, int64_t workspace_bytes,
+                         void* stream);
+
+/* ---- k-NN random geometric graph: create_data (eval_gnn.py:150-165) ------------------------- */
+/* Upper bound of edges graph g can emit: 4 * N_g * k1 (two k-NN sets, both directions). */
+int64_t gmp_knn_graph_max_edges(int64_t n_nodes, int k1);
+int64_t gmp_knn_graph_workspace_bytes(int64_t n_graphs, int64_t n_nodes_total, int64_t max_nodes_per_graph, int k1_max);
+/* For every graph: S = kNN_k1(all N_g nodes) U kNN_k1(first n_free_g nodes), self included
+ * (knn_graph(.., loop=True), eval_gnn.py:160,162); output = sorted unique of S U reverse(S) by key
+ * src*N+dst (coalesce, eval_gnn.py:164).  Distance: fp32 squared L2, left-to-right over dims,
+ * ties to the lower index.
+ *   v [N_total,c] f32; node_ptr_h [B+1]; n_free_h [B]; k1_h [B] (per graph, eval_gnn.py:159)
+ *   edge_index_out [2, edge_capacity] i64 (row stride = edge_capacity), graph g's edges are
+ *   written contiguously from column edge_ptr_out[g]; edge_ptr_out [B+1] i32 DEVICE (filled by the call).
+ * Returns GMP_E_INVALID if edge_capacity < sum_g 4*N_g*k1_g is not guaranteed to fit. */
+int gmp_knn_graph(gmp_handle* h, int64_t n_graphs, const float* v, int c, const int32_t* node_ptr_h,
+                  const int32_t* n_free_h, const int32_t* k1_h, int64_t* edge_index_out, int64_t edge_capacity,
+                  int32_t* edge_ptr_out, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- maze collision: MazeEnv (environment/maze_env.py, dim == 2) --------------------------- */
+/* Replaces MazeEnv._state_fp / _point_in_free_space (maze_env.py:270-277, 293-299), batched.
+ *   states [n,2] f32|f64 (dtype = GMP_DTYPE_*); maps [P,15,15] u8 (1 = occupied);
+ *   problem_of_state [n] i32 or NULL (= problem 0)
+ *   free_out [n] u8; counted_out [n] u8 nullable: 1 iff the reference would have incremented
+ *   collision_check_count (in-range states only, maze_env.py:272-276). */
+int gmp_maze_state_fp(const void* states, int dtype, const uint8_t* maps, const int32_t* problem_of_state,
+                      int64_t n, uint8_t* free_out, uint8_t* counted_out, void* stream);
+/* Replaces MazeEnv._edge_fp + _iterative_check_segment (maze_env.py:301-325), batched.
+ *   n_checks_out [n] i32 nullable: increments of collision_check_count the reference would make
+ *   for this edge (DFS order, early exit). */
+int gmp_maze_edge_fp(const void* a, const void* b, int dtype, const uint8_t* maps, const int32_t* problem_of_edge,
+                     int64_t n, uint8_t* free_out, int32_t* n_checks_out, void* stream);
+/* Same check for every edge of a packed batch of graphs, endpoints gathered from v (f32):
+ * edge e of graph g tests v[node_ptr[g]+src] -> v[node_ptr[g]+dst] against maps[problem_of_graph[g]]
+ * (what eval_gnn.py:215 does one edge at a time).  node_ptr / edge_ptr / problem_of_graph are DEVICE
+ * arrays here ([B+1],[B+1],[B] i32; problem_of_graph NULL = graph index). */
+int gmp_maze_edge_fp_graph(const float* v, const int64_t* edge_index, int64_t edge_row_stride, const int32_t* node_ptr,
+                           const int32_t* edge_ptr, const int32_t* problem_of_graph, int64_t n_graphs,
+                           int64_t n_edges_total, const uint8_t* maps, uint8_t* free_out, int32_t* n_checks_out,
+                           void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GNNMP_H_ */

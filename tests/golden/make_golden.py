@@ -85,7 +85,7 @@ def main():
 
     # ---------------------------------------------------------------- maze problems subset
     env = MazeEnv(dim=2)
-    prob_ids = np.array([0, 1, 2, 3, 7, 100, 2000, 2001, 2500, 2999])
+    prob_ids = np.array([0, 1, 2, 3, 7, 100, 2000, 2001, 2002, 2003, 2004, 2005, 2500, 2999])
     np.savez_compressed(os.path.join(HERE, "maze_problems.npz"),
                         ids=prob_ids, maps=env.maps[prob_ids].astype(np.uint8),
                         init_states=env.init_states[prob_ids], goal_states=env.goal_states[prob_ids])

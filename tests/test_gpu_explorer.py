@@ -1,0 +1,115 @@
+"""GPU: explorer forward through the C ABI vs golden (reference model.py) and vs the oracle; 1e-4 on logits."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOL = 1e-4  # BASELINE.json north_star: "edge logits within 1e-4 fp32"
+
+CASES = [("maze2", "weights_maze.pt", (2, 2, 32, 2)), ("kuka7", "weights_kuka.pt", (3, 7, 64, 6)),
+         ("kuka14", "kuka_14.pt", (3, 14, 32, 6))]
+
+
+def make_model(wfile, dims, dev):
+    from gnn_motion_planning_b200.model import EncoderProcessDecoder
+    m = EncoderProcessDecoder(workspace_size=dims[0], config_size=dims[1], embed_size=dims[2], obs_size=dims[3]).to(dev)
+    m.load_state_dict(torch.load(os.path.join(G, "weights", wfile), map_location="cpu"))
+    return m.eval()
+
+
+@pytest.mark.parametrize("tag,wfile,dims", CASES)
+def test_forward_golden(cuda_device, tag, wfile, dims):
+    ex = np.load(os.path.join(G, "explorer.npz"))
+    m = make_model(wfile, dims, cuda_device)
+    v = torch.from_numpy(ex[tag + "_v"]).to(cuda_device)
+    ei = torch.from_numpy(ex[tag + "_edge_index"]).to(cuda_device)
+    obs = torch.from_numpy(ex[tag + "_obstacles"]).to(cuda_device)
+    goal = torch.from_numpy(ex[tag + "_goal"]).to(cuda_device)
+    for loop in (1, 5):
+        dense = m(goal=goal, loop=loop, v=v, obstacles=obs, free=None, collided=None, edge_index=ei, labels=None)
+        assert dense.shape == (len(v), len(v)) and dense.dtype == torch.float32 and dense.is_cuda
+        got = dense[ei[1], ei[0]].cpu().numpy()
+        want = ex["%s_logits_loop%d" % (tag, loop)]
+        assert np.abs(got - want).max() < TOL, (tag, loop, np.abs(got - want).max())
+        mask = torch.zeros_like(dense, dtype=torch.bool)
+        mask[ei[1], ei[0]] = True
+        assert float(dense[~mask].abs().max()) == 0.0                  # zeros off the edge set (model.py:148)
+        sp = m.forward_sparse(goal=goal, loop=loop, v=v, obstacles=obs, edge_index=ei)
+        assert torch.equal(sp, dense[ei[1], ei[0]])
+    m.use_obstacles = False                                            # poked from outside, eval_gnn.py:88
+    got = m.forward_sparse(goal=goal, loop=5, v=v, obstacles=obs, edge_index=ei).cpu().numpy()
+    assert np.abs(got - ex[tag + "_logits_noobs"]).max() < TOL
+
+
+@pytest.mark.parametrize("tag,wfile,dims", CASES)
+def test_batched_ragged_vs_oracle(cuda_device, tag, wfile, dims):
+    """A ragged packed batch (different N, E, O per graph, one graph without obstacles, unsorted non-symmetric edges)."""
+    from oracle import explorer as o_explorer
+    from oracle import knn_graph as o_knn
+    sd = torch.load(os.path.join(G, "weights", wfile), map_location="cpu")
+    m = make_model(wfile, dims, cuda_device)
+    c, s = dims[1], dims[3]
+    rng = np.random.default_rng(42)
+    graphs = []
+    for n, k, o in [(300, 12, 70 if s == 2 else 9), (40, 5, 0), (513, 9, 33 if s == 2 else 1), (129, 20, 5)]:
+        v = rng.uniform(-1, 1, (n, c)).astype(np.float32)
+        ei = o_knn.knn_graph_edges(v, n, k)
+        if n == 129:   # arbitrary COO: shuffled order, a few edges dropped (not symmetric)
+            keep = rng.permutation(ei.shape[1])[: ei.shape[1] - 17]
+            ei = ei[:, keep]
+        obs = rng.uniform(-0.5, 0.5, (o, s)).astype(np.float32)
+        graphs.append((v, ei, v[1].copy(), obs))
+    node_ptr = np.cumsum([0] + [len(g[0]) for g in graphs])
+    edge_ptr = np.cumsum([0] + [g[1].shape[1] for g in graphs])
+    obs_ptr = np.cumsum([0] + [len(g[3]) for g in graphs])
+    V = torch.from_numpy(np.concatenate([g[0] for g in graphs])).to(cuda_device)
+    EI = torch.from_numpy(np.concatenate([g[1] for g in graphs], 1)).to(cuda_device)
+    GOAL = torch.from_numpy(np.stack([g[2] for g in graphs])).to(cuda_device)
+    OBS = torch.from_numpy(np.concatenate([g[3] for g in graphs])).to(cuda_device)
+    logits, dense = m.forward_batch(V, EI, GOAL, OBS, node_ptr, edge_ptr, obs_ptr, loop=5, dense=True)
+    logits = logits.cpu().numpy()
+    dense = dense.cpu().numpy()
+    doff = np.cumsum([0] + [len(g[0]) ** 2 for g in graphs])
+    for g, (v, ei, goal, obs) in enumerate(graphs):
+        want = o_explorer.explorer_forward(sd, torch.from_numpy(v), torch.from_numpy(ei), torch.from_numpy(goal),
+                                           torch.from_numpy(obs), loop=5, dense=False).numpy()
+        got = logits[edge_ptr[g]:edge_ptr[g + 1]]
+        assert np.abs(got - want).max() < TOL, (tag, g, np.abs(got - want).max())
+        d = dense[doff[g]:doff[g + 1]].reshape(len(v), len(v))
+        assert np.array_equal(d[ei[1], ei[0]], got)
+        assert np.count_nonzero(d) <= ei.shape[1]
+
+
+def test_error_budget_vs_fp64(cuda_device):
+    """The kernel's error against the fp64 arbiter is of the same order as the reference fp32 path's own error."""
+    from oracle import explorer as o_explorer
+    ex = np.load(os.path.join(G, "explorer.npz"))
+    sd = torch.load(os.path.join(G, "weights", "weights_maze.pt"), map_location="cpu")
+    m = make_model("weights_maze.pt", (2, 2, 32, 2), cuda_device)
+    v, ei = torch.from_numpy(ex["maze2_v"]), torch.from_numpy(ex["maze2_edge_index"])
+    obs, goal = torch.from_numpy(ex["maze2_obstacles"]), torch.from_numpy(ex["maze2_goal"])
+    f64 = o_explorer.explorer_forward(sd, v, ei, goal, obs, loop=5, dense=False, dtype=torch.float64).numpy()
+    got = m.forward_sparse(goal=goal.to(cuda_device), loop=5, v=v.to(cuda_device), obstacles=obs.to(cuda_device),
+                           edge_index=ei.to(cuda_device)).cpu().numpy()
+    ref_err = np.abs(ex["maze2_logits_loop5"] - f64).max()
+    our_err = np.abs(got - f64).max()
+    print("max |err| vs fp64: reference fp32 %.3g, kernel %.3g" % (ref_err, our_err))
+    assert our_err < 5e-5
+
+
+def test_errors(cuda_device):
+    from gnn_motion_planning_b200 import _lib
+    m = make_model("weights_maze.pt", (2, 2, 32, 2), cuda_device)
+    v = torch.zeros(10, 2, device=cuda_device)
+    ei = torch.tensor([[0, 1], [1, 12]], device=cuda_device)
+    with pytest.raises(IndexError):
+        m(goal=v[0], loop=1, v=v, obstacles=torch.zeros(3, 2, device=cuda_device), edge_index=ei)
+    with pytest.raises(_lib.GnnmpError):
+        m.forward_batch(torch.zeros(10, 2), ei.cpu(), v[:1], None, [0, 10], [0, 2], [0, 0])
+    # empty edge set / single node
+    out = m(goal=v[0], loop=2, v=v[:1], obstacles=torch.zeros(0, 2, device=cuda_device),
+            edge_index=torch.zeros(2, 0, dtype=torch.int64, device=cuda_device))
+    assert out.shape == (1, 1) and float(out.abs().sum()) == 0.0

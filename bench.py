@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""bench.py -- the driver-facing benchmark of the B200 hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload C2|C3|C4]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the hot path over one batch of synthetic planning problems:
+    k-NN RGG construction (gmp_knn_graph)  ->  explorer forward (gmp_explorer_forward)  ->
+    collision check of every edge of every graph (gmp_maze_edge_fp_graph; maze workloads)
+Workload at N=1 is BASELINE.json configs[1]: 2-D maze, batch = 256 problems, 1000-node k=50 RGG,
+shipped weights_maze.pt, loop = 5, obstacles = occupied cells of real maze maps.
+Multi-GPU: the batch of independent problems is sharded, 256 problems per rank (weak scaling); the only
+collective is the all-gather of the per-problem result rows at the end of a step.
+
+Prints ONE JSON line (rank 0).  `--impl reference` times the CPU oracle (the reference's PyG path cannot be
+installed here) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+G = os.path.join(ROOT, "tests", "golden")
+
+WORKLOADS = {
+    # name: env, c, e, s, ws, N, k, batch per GPU, weights
+    "C2": dict(env="maze2", c=2, e=32, s=2, ws=2, n=1000, k=50, batch=256, weights="weights_maze.pt", lo=-1.0, hi=1.0),
+    "C3": dict(env="kuka7", c=7, e=64, s=6, ws=3, n=1000, k=50, batch=256, weights="weights_kuka.pt", lo=-2.9, hi=2.9),
+    "C4": dict(env="kuka14", c=14, e=32, s=6, ws=3, n=2000, k=50, batch=128, weights="kuka_14.pt", lo=-2.9, hi=2.9),
+}
+
+
+def make_problem(wl, g):
+    """Synthetic problem g of the workload: node 0 = init, node 1 = goal, all nodes free."""
+    rng = np.random.default_rng(1234 + g)
+    v = rng.uniform(wl["lo"], wl["hi"], (wl["n"], wl["c"])).astype(np.float32)
+    if wl["s"] == 2:
+        maps = np.load(os.path.join(G, "maze_maps_256.npz"))["maps"]
+        occ = np.argwhere(maps[g % len(maps)] == 1)
+        obs = (occ / 15.0 - 0.5).astype(np.float32)
+    else:
+        nb = 2 + g % 8
+        obs = np.concatenate([rng.uniform(0.1, 0.3, (nb, 3)), rng.uniform(-0.8, 0.8, (nb, 3))], 1).astype(np.float32)
+    return v, obs
+
+
+def ref_oplist_flops(n, e_cnt, o, c, e, s, loop=5):
+    from oracle.explorer import flops_per_graph
+    return flops_per_graph(n, e_cnt, o, c, e, s, loop)
+
+
+def edge_feature_flops(e_cnt, o, c, e):
+    """Algorithmic FLOPs of what ONE edge_feature_kernel launch produces, reference formulation (model.py:120,123,
+    130 + the edge columns of lin_0[0] and policy[0]), excluding the obstacle-token side."""
+    enc = 2 * 2 * e_cnt * (2 * c * e + e * e)
+    blk = 2 * (3 * e_cnt * e * e + 2 * e_cnt * (o + 1) * e + 2 * e_cnt * e * e)
+    return enc + 3 * blk + 2 * e_cnt * 2 * e * e + 2 * e_cnt * e * e
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.lines = []
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=2)
+        except Exception:
+            self.p.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nme, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle (restated reference) on the host cores
+# --------------------------------------------------------------------------------------------------------------
+def cpu_graphs_per_sec(wl, graph_ids, threads):
+    import torch
+    from oracle import explorer as o_explorer, knn_graph as o_knn, maze as o_maze
+    torch.set_num_threads(threads)
+    sd = torch.load(os.path.join(G, "weights", wl["weights"]), map_location="cpu")
+    maps = np.load(os.path.join(G, "maze_maps_256.npz"))["maps"]
+    t0 = time.perf_counter()
+    n_edges = 0
+    for g in graph_ids:
+        v, obs = make_problem(wl, g)
+        ei = o_knn.knn_graph_edges(v, wl["n"], wl["k"])
+        o_explorer.explorer_forward(sd, torch.from_numpy(v), torch.from_numpy(ei), torch.from_numpy(v[1]),
+                                    torch.from_numpy(obs), loop=5, dense=False)
+        if wl["env"] == "maze2":
+            o_maze.edge_fp(v[ei[0]], v[ei[1]], maps, np.full(ei.shape[1], g % len(maps), np.int32))
+        n_edges += ei.shape[1]
+    dt = time.perf_counter() - t0
+    return len(graph_ids) / dt, dt, n_edges
+
+
+def run_reference(args, wl, rank, world):
+    if rank != 0:
+        return
+    import torch
+    threads = os.cpu_count() or 1
+    per_step = args.ref_graphs_per_step
+    for w in range(args.warmup):
+        cpu_graphs_per_sec(wl, [w % 4], threads)
+    t = []
+    for k in range(args.steps):
+        gps, dt, _ = cpu_graphs_per_sec(wl, list(range(k * per_step, (k + 1) * per_step)), threads)
+        t.append(dt)
+    ms = 1000.0 * float(np.mean(t))
+    value = per_step / (ms / 1000.0)
+    sample = "%d of the %d graphs of the workload per step (knn graph + explorer forward + edge checks, oracle port)" % (
+        per_step, wl["batch"])
+    line = {
+        "impl": "reference", "metric": "explorer_graphs_per_sec", "value": value, "unit": "graphs/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, wl, world),
+        "cpu_baseline": {"value": value, "unit": "graphs/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference PyG path not installable (torch_geometric/torch_cluster/torch_sparse absent, no network): "
+                "timed the oracle restatement of eval_gnn.create_data + model.py forward + maze_env._edge_fp on the host cores",
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, wl, world):
+    return {"workload": "%s: %s, batch=%d problems/GPU, %d-node k=%d RGG, loop=5, shipped %s" % (
+        args.workload, wl["env"], wl["batch"], wl["n"], wl["k"], wl["weights"]),
+        "step": "knn_graph + explorer_forward + edge collision check of all edges", "global_batch": wl["batch"] * world,
+        "parallelism": "dp%d (independent problems sharded, all-gather of result rows only)" % world,
+        "l2": "per-step working set (~3.8 GB of edge features) >> 126 MB L2; no explicit flush needed"}
+
+
+# --------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--ref-graphs-per-step", type=int, default=4)
+    ap.add_argument("--cpu-sample", type=int, default=16)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    wl = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, wl, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from gnn_motion_planning_b200 import _lib, collision, graph
+    from gnn_motion_planning_b200.model import EncoderProcessDecoder
+
+    _lib.load()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    B, N, c = wl["batch"], wl["n"], wl["c"]
+    # ---- synthetic inputs of this rank's shard (problems rank*B .. rank*B+B-1), host side
+    vs, obss = zip(*[make_problem(wl, rank * B + g) for g in range(B)])
+    v_h = torch.from_numpy(np.concatenate(vs)).pin_memory()
+    goal_h = torch.from_numpy(np.stack([x[1] for x in vs])).pin_memory()
+    obs_h = torch.from_numpy(np.concatenate(obss)).pin_memory()
+    node_ptr = (np.arange(B + 1) * N).astype(np.int32)
+    obs_ptr = np.cumsum([0] + [len(o) for o in obss]).astype(np.int32)
+    n_free = np.full(B, N, np.int32)
+    k1 = np.full(B, wl["k"], np.int32)
+    maps_np = np.load(os.path.join(G, "maze_maps_256.npz"))["maps"]
+    maps_h = torch.from_numpy(np.ascontiguousarray(maps_np)).pin_memory()
+    prob_h = torch.from_numpy(((rank * B + np.arange(B)) % len(maps_np)).astype(np.int32)).pin_memory()
+    is_maze = wl["env"] == "maze2"
+
+    model = EncoderProcessDecoder(workspace_size=wl["ws"], config_size=c, embed_size=wl["e"], obs_size=wl["s"]).to(dev)
+    model.load_state_dict(torch.load(os.path.join(G, "weights", wl["weights"]), map_location="cpu"))
+    model.eval()
+    model.set_timing(True)
+
+    # ---- device-resident copies for the kernel-only measurement
+    v_d, goal_d, obs_d = v_h.to(dev), goal_h.to(dev), obs_h.to(dev)
+    maps_d, prob_d = maps_h.to(dev), prob_h.to(dev)
+    node_ptr_d = torch.from_numpy(node_ptr).to(dev)
+    cap = int(sum(_lib.load().gmp_knn_graph_max_edges(N, int(wl["k"])) for _ in range(B)))
+    ei_buf = torch.empty((2, cap), dtype=torch.int64, device=dev)
+    logits_buf = torch.empty(cap, dtype=torch.float32, device=dev)
+    free_buf = torch.empty(cap, dtype=torch.uint8, device=dev)
+    checks_buf = torch.empty(cap, dtype=torch.int32, device=dev)
+    rows_buf = torch.empty((B, 4), dtype=torch.float32, device=dev)
+    gather_buf = torch.empty((world, B, 4), dtype=torch.float32, device=dev) if world > 1 else None
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    phase_ms = {}
+    state = {}
+
+    def step(v, goal, obs, maps, prob, timed=False):
+        e0, e1, e2, e3 = ev(), ev(), ev(), ev()
+        e0.record()
+        ei, edge_ptr = graph.knn_graph_batch(v, node_ptr, n_free, k1, edge_index_out=ei_buf)   # syncs on edge_ptr (B+1 ints)
+        e1.record()
+        et = int(edge_ptr[-1])
+        logits = model.forward_batch(v, ei, goal, obs, node_ptr, edge_ptr, obs_ptr, loop=5, dense=False, out=logits_buf)
+        e2.record()
+        edge_ptr_d = torch.from_numpy(edge_ptr).to(dev, non_blocking=True)
+        if is_maze:
+            collision.maze_edge_fp_graph(v, ei, node_ptr_d, edge_ptr_d, maps, et, problem_of_graph=prob, want_checks=True,
+                                         free_out=free_buf, checks_out=checks_buf)
+        e3.record()
+        # per-problem result rows: (problem id, E_g, #collision-free edges, best logit) -> the only collective
+        rows = collision.result_rows(logits, free_buf if is_maze else None, edge_ptr_d, rank * B, out=rows_buf)
+        if world > 1:
+            dist.all_gather_into_tensor(gather_buf.view(world * B, 4), rows)
+        state.update(et=et, edge_ptr=edge_ptr, rows=rows, ei=ei)
+        if timed:
+            torch.cuda.current_stream().synchronize()
+            for k_, v_ in model.last_timings().items():
+                phase_ms[k_] = phase_ms.get(k_, 0.0) + v_
+            phase_ms["knn_graph"] = phase_ms.get("knn_graph", 0.0) + e0.elapsed_time(e1)
+            phase_ms["explorer_forward"] = phase_ms.get("explorer_forward", 0.0) + e1.elapsed_time(e2)
+            phase_ms["collision"] = phase_ms.get("collision", 0.0) + e2.elapsed_time(e3)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_region(fn, steps):
+        barrier()
+        a, b = ev(), ev()
+        a.record()
+        for _ in range(steps):
+            fn()
+        b.record()
+        barrier()
+        ms = torch.tensor([a.elapsed_time(b)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / steps
+
+    # ---- kernel-only: inputs resident in HBM
+    for _ in range(args.warmup):
+        step(v_d, goal_d, obs_d, maps_d, prob_d)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms_step = timed_region(lambda: step(v_d, goal_d, obs_d, maps_d, prob_d, timed=True), args.steps)
+    clocks = sampler.stop() if sampler else None
+    et = state["et"]
+    n_free_edges = float(state["rows"][:, 2].sum()) if is_maze else None
+    checks_total = int(checks_buf[:et].sum()) if is_maze else None
+
+    # ---- end to end: host (pinned) buffers in, host buffers out, copies inside the timed region
+    out_logits_h = torch.empty(cap, dtype=torch.float32).pin_memory()
+    out_free_h = torch.empty(cap, dtype=torch.uint8).pin_memory()
+    out_ei_h = torch.empty((2, cap), dtype=torch.int64).pin_memory()
+    in_bufs = [torch.empty_like(v_d), torch.empty_like(goal_d), torch.empty_like(obs_d), torch.empty_like(maps_d), torch.empty_like(prob_d)]
+    io = {}
+
+    def e2e_step():
+        for d, h in zip(in_bufs, (v_h, goal_h, obs_h, maps_h, prob_h)):
+            d.copy_(h, non_blocking=True)
+        step(*in_bufs)
+        n = state["et"]
+        out_logits_h[:n].copy_(logits_buf[:n], non_blocking=True)
+        out_free_h[:n].copy_(free_buf[:n], non_blocking=True)
+        out_ei_h[0, :n].copy_(ei_buf[0, :n], non_blocking=True)   # two contiguous row copies
+        out_ei_h[1, :n].copy_(ei_buf[1, :n], non_blocking=True)
+        torch.cuda.current_stream().synchronize()   # the caller owns the results only after this
+        io["h2d"] = sum(h.numel() * h.element_size() for h in (v_h, goal_h, obs_h, maps_h, prob_h))
+        io["d2h"] = n * (4 + 1 + 16) + (B + 1) * 4
+
+    for _ in range(2):
+        e2e_step()
+    ms_e2e = timed_region(e2e_step, args.steps)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    K = args.steps
+    graphs_per_s = B * world / (ms_step / 1000.0)
+    o_mean = float(np.mean(np.diff(obs_ptr)))
+    e_mean = et / B
+    ef_ms = phase_ms["edge_feature"] / K
+    ef_flops = sum(edge_feature_flops(int(ne), int(no), c, wl["e"]) for ne, no in zip(np.diff(state["edge_ptr"]), np.diff(obs_ptr)))
+    fwd_flops = sum(ref_oplist_flops(N, int(ne), int(no), c, wl["e"], wl["s"]) for ne, no in zip(np.diff(state["edge_ptr"]), np.diff(obs_ptr)))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)"
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    ef_tflops = ef_flops / (ef_ms * 1e-3) / 1e12
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1900.0
+    fp32_peak_tf = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+    msg_ms = phase_ms["edge_msg"] / K / 5.0
+    msg_bytes = et * wl["e"] * 4 + et * (2 * wl["e"] * 4 + 8)   # P stream + gathered A[src], B[dst] rows + csr ids (L2-resident gathers)
+    line = {
+        "metric": "explorer_graphs_per_sec", "value": graphs_per_s, "unit": "graphs/s", "n_gpus": world, "steps": K,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": workload_config(args, wl, world),
+        "edges_per_graph": e_mean, "obstacles_per_graph": o_mean,
+        "phases_ms_per_step": {k_: v_ / K for k_, v_ in sorted(phase_ms.items())},
+        "explorer_forward_graphs_per_sec": B * world / (phase_ms["explorer_forward"] / K / 1e3),
+        "collision_checks_per_sec": (et * world / (phase_ms["collision"] / K / 1e3)) if is_maze else None,
+        "collision_lookups_per_edge": (checks_total / et) if is_maze else None,
+        "knn_graphs_per_sec": B * world / (phase_ms["knn_graph"] / K / 1e3),
+        "forward_tflops_ref_oplist": fwd_flops / (phase_ms["explorer_forward"] / K / 1e3) / 1e12,
+        "roofline": {"kernel": "edge_feature_kernel<%d,%d>" % (c, wl["e"]), "bound": "tensor", "achieved": ef_tflops, "peak": peak_tf,
+                     "unit": "TFLOP/s", "frac": ef_tflops / peak_tf, "traffic": None, "peak_source": peak_src,
+                     "ms_per_launch": ef_ms, "algorithmic_gflop_per_launch": ef_flops / 1e9,
+                     "note": "fp32 FMA kernel (1e-4 logit tolerance rules out 1-pass TF32/BF16); vs fp32 SIMT peak "
+                             "148 SM x 128 FMA x %.0f MHz = %.1f TFLOP/s the fraction is %.3f" % (sm_mhz, fp32_peak_tf, ef_tflops / fp32_peak_tf)},
+        "roofline_hbm_kernel": {"kernel": "edge_msg_kernel<%d>" % wl["e"], "bound": "hbm", "achieved": msg_bytes / (msg_ms * 1e-3) / 1e9,
+                                "peak": hbm, "unit": "GB/s", "frac": msg_bytes / (msg_ms * 1e-3) / 1e9 / hbm, "traffic": None,
+                                "ms_per_launch": msg_ms},
+        "e2e": {"value": B * world / (ms_e2e / 1000.0), "unit": "graphs/s", "h2d_bytes_per_step": io["h2d"], "d2h_bytes_per_step": io["d2h"],
+                "ms_per_step": ms_e2e},
+        "gpu_launches": K * (5 + 3 + 1 + 1 + 1 + 1 + 6 + 5 + 1 + 1 + (1 if is_maze else 0)),
+        "gpu_launches_note": "per step: knn 5 (select,row_count,row_scan,graph_scan,emit) + csr 3 + goal_index + obstacle + node_pre + "
+                             "edge_feature + node_loop x6 + edge_msg x5 + policy + maze_edge_graph + result_rows; memsets/copies not counted",
+        "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        gps, dt, _ = cpu_graphs_per_sec(wl, list(range(args.cpu_sample)), threads)
+        line["cpu_baseline"] = {"value": gps, "unit": "graphs/s", "cores": threads, "kind": "port",
+                                "sample": "first %d graphs of the workload (oracle: knn graph + explorer forward + edge checks), %.1f s" % (args.cpu_sample, dt)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

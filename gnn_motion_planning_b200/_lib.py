@@ -26,6 +26,8 @@ SIGNATURES = {
     "gmp_explorer_workspace_bytes": (c_int64, [c_void_p, c_int64, c_int64, c_int64, c_int64]),
     "gmp_explorer_forward": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "gmp_set_timing": (c_int, [c_void_p, c_int]),
+    "gmp_get_timings": (c_int, [c_void_p, c_void_p, c_int]),
     "gmp_knn_graph_max_edges": (c_int64, [c_int64, c_int]),
     "gmp_knn_graph_workspace_bytes": (c_int64, [c_int64, c_int64, c_int64, c_int]),
     "gmp_knn_graph": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
@@ -34,6 +36,7 @@ SIGNATURES = {
     "gmp_maze_edge_fp": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "gmp_maze_edge_fp_graph": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
                                        c_void_p, c_void_p, c_void_p, c_void_p]),
+    "gmp_result_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p]),
 }
 
 _lib = None

@@ -76,3 +76,14 @@ def maze_edge_fp_graph(v, edge_index, node_ptr_d, edge_ptr_d, maps, n_edges_tota
                                           _lib.ptr(edge_ptr_d), _lib.ptr(problem_of_graph), B, n_edges_total,
                                           _lib.ptr(maps), _lib.ptr(free), _lib.ptr(checks), _lib.stream_ptr(v.device)))
     return (free, checks) if want_checks else free
+
+
+@torch.no_grad()
+def result_rows(logits, edge_free, edge_ptr_d, first_problem_id=0, out=None):
+    """Per-problem result rows [B,4] = (problem id, E_g, #free edges, best logit) -- the all-gather payload."""
+    lib = _lib.load()
+    B = edge_ptr_d.numel() - 1
+    rows = out if out is not None else torch.empty((B, 4), dtype=torch.float32, device=logits.device)
+    _lib.check(lib.gmp_result_rows(_lib.ptr(logits), _lib.ptr(edge_free), _lib.ptr(edge_ptr_d), B, int(first_problem_id),
+                                   _lib.ptr(rows), _lib.stream_ptr(logits.device)))
+    return rows

@@ -1071,7 +1071,10 @@ int run_forward(gmp_handle* h, int64_t B, const float* v, const int64_t* edge_in
   const float* W = m.d_weights;
   const int64_t table_stride = obs_tiles * 2 * E * OT;
 
+  Timeline& tl = h->tl;
+  tl.reset();
   // CSR by target
+  tl.begin(kPhCsr, st);
   if (Nt > 0) GMP_CUDA(cudaMemsetAsync(ws.indeg, 0, (Nt + 1) * sizeof(int32_t), st));
   if (Et > 0) {
     int gx = (int)std::min<int64_t>((Et + 255) / 256, kNumSMs * 16);
@@ -1086,44 +1089,59 @@ int run_forward(gmp_handle* h, int64_t B, const float* v, const int64_t* edge_in
                                         ws.csr_src, ws.csr_dst, ws.csr_eid);
     GMP_LAUNCH_CHECK();
   }
+  tl.end(st);
+  tl.begin(kPhGoal, st);
   goal_index_kernel<<<(int)B, 256, 0, st>>>(v, goal, C, ws.node_ptr, ws.goal_idx);
   GMP_LAUNCH_CHECK();
+  tl.end(st);
+  tl.begin(kPhObstacle, st);
   if (use_obstacles && obs_tiles > 0) {
     const int n_slots = (int)(obs_tiles * OT);
     obstacle_kernel<S, E><<<dim3((n_slots + R - 1) / R, 2), kRtThreads, smem, st>>>(m.w, W, obstacles, ws.obs_ptr, ws.obs_tile_ptr,
                                                                                   (int)B, n_slots, ws.tables, table_stride);
     GMP_LAUNCH_CHECK();
   }
+  tl.end(st);
+  tl.begin(kPhNodePre, st);
   if (tile_n[B] > 0) {
     node_pre_kernel<C, E><<<tile_n[B], kRtThreads, smem, st>>>(m.w, W, v, goal, ws.node_ptr, ws.tile_ptr_n, (int)B, ws.obs_ptr,
                                                               ws.obs_tile_ptr, ws.tables, table_stride, use_obstacles, ws.goal_idx,
                                                               ws.X0, ws.D0, ws.H);
     GMP_LAUNCH_CHECK();
   }
+  tl.end(st);
+  tl.begin(kPhEdgeFeature, st);
   if (tile_e[B] > 0) {
     edge_feature_kernel<C, E><<<tile_e[B], kRtThreads, smem, st>>>(m.w, W, v, ws.csr_src, ws.csr_dst, ws.edge_ptr, ws.tile_ptr_e,
                                                                   (int)B, ws.obs_ptr, ws.obs_tile_ptr, ws.tables, table_stride,
                                                                   use_obstacles, ws.P, ws.Q);
     GMP_LAUNCH_CHECK();
   }
+  tl.end(st);
   const int node_tiles = (int)((Nt + R - 1) / R), slot_tiles = (int)((Et + R - 1) / R);
   for (int it = 0; it <= loop; ++it) {
     const int mode = it == loop ? 2 : (it == 0 ? 0 : 1);
     if (node_tiles > 0) {
+      tl.begin(kPhNodeLoop, st);
       node_loop_kernel<E><<<node_tiles, kRtThreads, smem, st>>>(m.w, W, mode, (int)Nt, ws.X0, ws.D0, ws.H, ws.Xg, ws.AGG, ws.A, ws.B);
       GMP_LAUNCH_CHECK();
+      tl.end(st);
     }
     if (it < loop && slot_tiles > 0) {
+      tl.begin(kPhEdgeMsg, st);
       edge_msg_kernel<E><<<slot_tiles, kRtThreads, smem, st>>>(m.w, W, (int)Et, ws.csr_src, ws.csr_dst, ws.A, ws.B, ws.P, ws.AGG);
       GMP_LAUNCH_CHECK();
+      tl.end(st);
     }
   }
+  tl.begin(kPhPolicy, st);
   if (dense && dense_off[B] > 0) GMP_CUDA(cudaMemsetAsync(dense, 0, dense_off[B] * sizeof(float), st));
   if (slot_tiles > 0) {
     policy_kernel<E><<<slot_tiles, kRtThreads, smem, st>>>(m.w, W, (int)Et, ws.csr_src, ws.csr_dst, ws.csr_eid, ws.A, ws.B, ws.Q,
                                                           ws.edge_ptr, ws.node_ptr, ws.dense_off, (int)B, logits, dense);
     GMP_LAUNCH_CHECK();
   }
+  tl.end(st);
   return GMP_OK;
 }
 
@@ -1131,6 +1149,26 @@ int run_forward(gmp_handle* h, int64_t B, const float* v, const int64_t* edge_in
 }  // namespace gmp
 
 using namespace gmp;
+
+extern "C" int gmp_set_timing(gmp_handle* h, int enable) {
+  GMP_REQUIRE(h, "null handle");
+  h->tl.enabled = enable != 0;
+  h->tl.reset();
+  return GMP_OK;
+}
+
+extern "C" int gmp_get_timings(gmp_handle* h, float* ms_out_h, int n) {
+  GMP_REQUIRE(h && ms_out_h && n >= kNumPhases, "need room for 8 phases");
+  for (int i = 0; i < n; ++i) ms_out_h[i] = 0.f;
+  for (auto& s : h->tl.spans) {
+    if (!s.b) continue;
+    GMP_CUDA(cudaEventSynchronize(s.b));
+    float ms = 0.f;
+    GMP_CUDA(cudaEventElapsedTime(&ms, s.a, s.b));
+    ms_out_h[s.phase] += ms;
+  }
+  return kNumPhases;
+}
 
 extern "C" int gmp_explorer_init(gmp_handle* h, int config_size, int embed_size, int obs_size) {
   GMP_REQUIRE(h, "null handle");

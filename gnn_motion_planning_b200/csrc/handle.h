@@ -68,10 +68,43 @@ struct SmootherModel {
   int64_t n_weights = 0;
 };
 
+// Optional per-phase device timing: cudaEvents recorded on the launching stream around each phase of the
+// last explorer forward (bench.py's roofline numbers come from here, not from a profiler).
+enum Phase { kPhCsr = 0, kPhGoal, kPhObstacle, kPhNodePre, kPhEdgeFeature, kPhNodeLoop, kPhEdgeMsg, kPhPolicy, kNumPhases };
+
+struct Timeline {
+  bool enabled = false;
+  std::vector<cudaEvent_t> pool;
+  size_t used = 0;
+  struct Span { int phase; cudaEvent_t a, b; };
+  std::vector<Span> spans;
+  cudaEvent_t next() {
+    if (used == pool.size()) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      pool.push_back(e);
+    }
+    return pool[used++];
+  }
+  void reset() { used = 0; spans.clear(); }
+  void begin(int phase, cudaStream_t st) {
+    if (!enabled) return;
+    Span s{phase, next(), nullptr};
+    cudaEventRecord(s.a, st);
+    spans.push_back(s);
+  }
+  void end(cudaStream_t st) {
+    if (!enabled) return;
+    spans.back().b = next();
+    cudaEventRecord(spans.back().b, st);
+  }
+};
+
 }  // namespace gmp
 
 struct gmp_handle {
   int device = 0;
   gmp::ExplorerModel ex;
   gmp::SmootherModel sm;
+  gmp::Timeline tl;
 };

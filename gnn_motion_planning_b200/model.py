@@ -188,6 +188,21 @@ class EncoderProcessDecoder:
             self._ws = torch.empty(int(nbytes * 1.05) + 1024, dtype=torch.uint8, device=self._device)
         return self._ws
 
+    PHASES = ("csr_build", "goal_index", "obstacle_stream", "node_pre", "edge_feature", "node_loop", "edge_msg", "policy")
+
+    def set_timing(self, enable=True):
+        """Record CUDA events around every phase of subsequent forwards (see ``last_timings``)."""
+        self._ensure_uploaded()
+        _lib.check(_lib.load().gmp_set_timing(self._handle, int(bool(enable))))
+
+    def last_timings(self):
+        """dict phase -> milliseconds of the last forward (synchronises on its events)."""
+        ms = np.zeros(len(self.PHASES), np.float32)
+        rc = _lib.load().gmp_get_timings(self._handle, ms.ctypes.data, len(ms))
+        if rc < 0:
+            _lib.check(rc)
+        return dict(zip(self.PHASES, ms.tolist()))
+
     # ------------------------------------------------------------------ batched entry point (new capability)
     @torch.no_grad()
     def forward_batch(self, v, edge_index, goal, obstacles, node_ptr, edge_ptr, obs_ptr, loop=5, dense=False,

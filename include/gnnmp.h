@@ -84,6 +84,15 @@ int gmp_explorer_forward(gmp_handle* h, int64_t n_graphs, const float* v, const 
                          float* edge_logits_out, float* dense_out, void* workspace, int64_t workspace_bytes,
                          void* stream);
 
+/* Optional device-side timing of the last gmp_explorer_forward on this handle (replaces the reference's
+ * wall-clock Timer spans, environment/timer.py:6-25).  gmp_get_timings synchronises on the recorded events and
+ * writes milliseconds per phase into ms_out_h[0..7]:
+ *   0 csr build, 1 goal index, 2 obstacle stream, 3 node encoders+blocks, 4 edge encoders+blocks,
+ *   5 node updates (sum over rounds), 6 edge messages + max aggregation (sum over rounds), 7 policy head.
+ * Returns the number of phases (8) or a negative error. */
+int gmp_set_timing(gmp_handle* h, int enable);
+int gmp_get_timings(gmp_handle* h, float* ms_out_h, int n);
+
 /* ---- k-NN random geometric graph: create_data (eval_gnn.py:150-165) ------------------------- */
 /* Upper bound of edges graph g can emit: 4 * N_g * k1 (two k-NN sets, both directions). */
 int64_t gmp_knn_graph_max_edges(int64_t n_nodes, int k1);
@@ -121,6 +130,13 @@ int gmp_maze_edge_fp_graph(const float* v, const int64_t* edge_index, int64_t ed
                            const int32_t* edge_ptr, const int32_t* problem_of_graph, int64_t n_graphs,
                            int64_t n_edges_total, const uint8_t* maps, uint8_t* free_out, int32_t* n_checks_out,
                            void* stream);
+
+/* ---- per-problem result rows: the final reduction of eval_gnn (eval_gnn.py:120-134) ----------- */
+/* One row of 4 floats per graph: (first_problem_id + g, E_g, #edges with edge_free != 0, max edge logit).
+ * edge_ptr is a DEVICE array [B+1]; edge_free is nullable.  These rows are the only payload of the multi-GPU
+ * all-gather (torch.distributed / NCCL on the host side). */
+int gmp_result_rows(const float* edge_logits, const uint8_t* edge_free, const int32_t* edge_ptr, int64_t n_graphs,
+                    int32_t first_problem_id, float* rows_out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -36,6 +36,19 @@ SIGNATURES = {
     "gmp_maze_edge_fp": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "gmp_maze_edge_fp_graph": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
                                        c_void_p, c_void_p, c_void_p, c_void_p]),
+    "gmp_arm_model_count": (c_int, []),
+    "gmp_arm_model_info": (c_int, [c_int, c_void_p, c_void_p, c_void_p]),
+    "gmp_arm_state_fp": (c_int, [c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "gmp_arm_edge_fp": (c_int, [c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int64, ctypes.c_double,
+                                c_void_p, c_void_p, c_void_p]),
+    "gmp_arm_edge_fp_graph": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
+                                      c_void_p, c_void_p, ctypes.c_double, c_void_p, c_void_p, c_void_p]),
+    "gmp_smoother_init": (c_int, [c_void_p, c_int, c_int]),
+    "gmp_smoother_set_tensor": (c_int, [c_void_p, c_char_p, c_void_p, c_int64]),
+    "gmp_smoother_finalize": (c_int, [c_void_p]),
+    "gmp_smoother_workspace_bytes": (c_int64, [c_void_p, c_int64, c_int64, c_int64, c_int64]),
+    "gmp_smoother_forward": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
+                                     c_void_p, c_float, c_int, c_void_p, c_void_p, c_int64, c_void_p]),
     "gmp_result_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p]),
 }
 

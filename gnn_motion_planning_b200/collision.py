@@ -87,3 +87,86 @@ def result_rows(logits, edge_free, edge_ptr_d, first_problem_id=0, out=None):
     _lib.check(lib.gmp_result_rows(_lib.ptr(logits), _lib.ptr(edge_free), _lib.ptr(edge_ptr_d), B, int(first_problem_id),
                                    _lib.ptr(rows), _lib.stream_ptr(logits.device)))
     return rows
+
+
+# ------------------------------------------------------------------------------------------------ arms
+ARM_KUKA7, ARM_KUKA14, ARM_KUKA13 = 0, 1, 2
+
+
+def arm_model_info(model):
+    """-> (dof, lower [dof] f64, upper [dof] f64): KukaEnv.pose_range (kuka_env.py:57-60)."""
+    import ctypes
+    lib = _lib.load()
+    dof = ctypes.c_int32(0)
+    lo, hi = np.zeros(14), np.zeros(14)
+    _lib.check(lib.gmp_arm_model_info(int(model), ctypes.addressof(dof), lo.ctypes.data, hi.ctypes.data))
+    return dof.value, lo[:dof.value].copy(), hi[:dof.value].copy()
+
+
+def pack_boxes(problems_obstacles, device):
+    """list (per problem) of [(halfExtents[3], basePosition[3]), ...] -> (boxes [O_total,6] f64 cuda, box_ptr [P+1] i32 cuda)."""
+    rows, ptr = [], [0]
+    for obs in problems_obstacles:
+        for h, p in obs:
+            rows.append(np.concatenate([np.asarray(h, np.float64).reshape(3), np.asarray(p, np.float64).reshape(3)]))
+        ptr.append(len(rows))
+    boxes = torch.from_numpy(np.array(rows, np.float64).reshape(-1, 6)).to(device)
+    return boxes, torch.from_numpy(np.array(ptr, np.int32)).to(device)
+
+
+@torch.no_grad()
+def arm_state_fp(model, states, boxes, box_ptr, problem=None, want_counted=False):
+    _lib.require_cuda(states, "states")
+    lib = _lib.load()
+    _lib.handle(_dev_index(states))
+    if states.dtype not in _DT:
+        raise TypeError("states must be float32 or float64")
+    dof = arm_model_info(model)[0]
+    states = states.reshape(-1, dof).contiguous()
+    n = states.shape[0]
+    if problem is not None:
+        problem = problem.to(device=states.device, dtype=torch.int32).contiguous()
+    free = torch.empty(n, dtype=torch.uint8, device=states.device)
+    counted = torch.empty(n, dtype=torch.uint8, device=states.device) if want_counted else None
+    _lib.check(lib.gmp_arm_state_fp(int(model), _lib.ptr(states), _DT[states.dtype], _lib.ptr(boxes), _lib.ptr(box_ptr),
+                                    _lib.ptr(problem), n, _lib.ptr(free), _lib.ptr(counted), _lib.stream_ptr(states.device)))
+    return (free, counted) if want_counted else free
+
+
+@torch.no_grad()
+def arm_edge_fp(model, a, b, boxes, box_ptr, problem=None, rrt_eps=0.5, want_checks=False):
+    _lib.require_cuda(a, "a")
+    _lib.require_cuda(b, "b")
+    lib = _lib.load()
+    _lib.handle(_dev_index(a))
+    if a.dtype not in _DT or b.dtype != a.dtype:
+        raise TypeError("a and b must both be float32 or both float64")
+    dof = arm_model_info(model)[0]
+    a = a.reshape(-1, dof).contiguous()
+    b = b.reshape(-1, dof).contiguous()
+    n = a.shape[0]
+    if problem is not None:
+        problem = problem.to(device=a.device, dtype=torch.int32).contiguous()
+    free = torch.empty(n, dtype=torch.uint8, device=a.device)
+    checks = torch.empty(n, dtype=torch.int32, device=a.device) if want_checks else None
+    _lib.check(lib.gmp_arm_edge_fp(int(model), _lib.ptr(a), _lib.ptr(b), _DT[a.dtype], _lib.ptr(boxes), _lib.ptr(box_ptr),
+                                   _lib.ptr(problem), n, float(rrt_eps), _lib.ptr(free), _lib.ptr(checks),
+                                   _lib.stream_ptr(a.device)))
+    return (free, checks) if want_checks else free
+
+
+@torch.no_grad()
+def arm_edge_fp_graph(model, v, edge_index, node_ptr_d, edge_ptr_d, boxes, box_ptr, n_edges_total, rrt_eps=0.5,
+                      problem_of_graph=None, want_checks=False, free_out=None, checks_out=None):
+    lib = _lib.load()
+    _lib.handle(_dev_index(v))
+    B = node_ptr_d.numel() - 1
+    free = free_out if free_out is not None else torch.empty(n_edges_total, dtype=torch.uint8, device=v.device)
+    checks = checks_out
+    if want_checks and checks is None:
+        checks = torch.empty(n_edges_total, dtype=torch.int32, device=v.device)
+    _lib.check(lib.gmp_arm_edge_fp_graph(int(model), _lib.ptr(v), _lib.ptr(edge_index), edge_index.stride(0), _lib.ptr(node_ptr_d),
+                                         _lib.ptr(edge_ptr_d), _lib.ptr(problem_of_graph), B, n_edges_total, _lib.ptr(boxes),
+                                         _lib.ptr(box_ptr), float(rrt_eps), _lib.ptr(free), _lib.ptr(checks),
+                                         _lib.stream_ptr(v.device)))
+    return (free, checks) if want_checks else free

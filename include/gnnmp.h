@@ -131,6 +131,53 @@ int gmp_maze_edge_fp_graph(const float* v, const int64_t* edge_index, int64_t ed
                            int64_t n_edges_total, const uint8_t* maps, uint8_t* free_out, int32_t* n_checks_out,
                            void* stream);
 
+/* ---- arm collision: KukaEnv / Kuka2Env (environment/kuka_env.py, kuka_2arm_env.py) ------------- */
+/* The reference queries PyBullet contact points; this library substitutes its own geometric model (DESIGN.md:
+ * FK down the URDF joint chain, link hulls filled with inscribed spheres, boxes as AABBs) -- parity with PyBullet
+ * is UNPINNED, parity with oracle/arm.c is bit-exact.  model: 0 = kuka7 (kuka_env.py, model_0.urdf), 1 = kuka14
+ * (kuka_2arm_env.py: two arms at x = -0.5 / +0.5, arm-arm contacts), 2 = kuka13 (model_3.urdf).
+ *   boxes [O_total, 6] f64 = (halfExtents[3], basePosition[3]) as stored in maze_files/kukas_*.pkl; problem p owns
+ *   rows box_ptr[p] .. box_ptr[p+1] (DEVICE i32 array). */
+int gmp_arm_model_count(void);
+/* dof and joint limits (KukaEnv.pose_range, kuka_env.py:57-60) of a model; host outputs, nullable. */
+int gmp_arm_model_info(int model, int32_t* dof_out, double* lower_h, double* upper_h);
+/* Replaces _state_fp / _point_in_free_space (kuka_env.py:354-376).  counted_out: 1 iff collision_check_count
+ * would be incremented (every state within joint limits, both outcomes). */
+int gmp_arm_state_fp(int model, const void* states, int dtype, const double* boxes, const int32_t* box_ptr,
+                     const int32_t* problem_of_state, int64_t n, uint8_t* free_out, uint8_t* counted_out, void* stream);
+/* Replaces _edge_fp (kuka_env.py:389-411): endpoints valid + free, then K = int(||b-a|| / rrt_eps) interpolated
+ * states k = 0..K-1, in the input dtype.  n_checks_out = collision_check_count increments. */
+int gmp_arm_edge_fp(int model, const void* a, const void* b, int dtype, const double* boxes, const int32_t* box_ptr,
+                    const int32_t* problem_of_edge, int64_t n, double rrt_eps, uint8_t* free_out, int32_t* n_checks_out,
+                    void* stream);
+/* Same for every edge of a packed batch of graphs (endpoints gathered from v f32, as eval_gnn.py:215 does one at a
+ * time); node_ptr / edge_ptr / problem_of_graph are DEVICE arrays (problem_of_graph NULL = graph index). */
+int gmp_arm_edge_fp_graph(int model, const float* v, const int64_t* edge_index, int64_t edge_row_stride,
+                          const int32_t* node_ptr, const int32_t* edge_ptr, const int32_t* problem_of_graph,
+                          int64_t n_graphs, int64_t n_edges_total, const double* boxes, const int32_t* box_ptr,
+                          double rrt_eps, uint8_t* free_out, int32_t* n_checks_out, void* stream);
+
+/* ---- smoother: ModelSmoother (model_smoother.py:46-142) --------------------------------------- */
+int gmp_smoother_init(gmp_handle* h, int config_size /*c*/, int embed_size /*128*/);
+/* load_state_dict (eval_gnn.py:104) by reference tensor name, e.g. "node_code.1.running_mean"; dead tensors ignored. */
+int gmp_smoother_set_tensor(gmp_handle* h, const char* name, const float* data_h, int64_t numel);
+int gmp_smoother_finalize(gmp_handle* h);
+int64_t gmp_smoother_workspace_bytes(const gmp_handle* h, int64_t n_problems, int64_t n_path_total, int64_t n_sample_total,
+                                     int64_t n_edges_total);
+/* Replaces ModelSmoother.forward (model_smoother.py:104-142) for a packed batch of problems.
+ *   path     [P_total, c] f32   waypoints, problem g owns rows path_ptr_h[g] .. path_ptr_h[g+1]     (`path`)
+ *   samples  [S_total, c] f32   cat(free, collided) per problem, rows sample_ptr_h[g] ..; the first n_free_h[g]
+ *                               rows of a problem are `free`, the rest `collided`                  (`free`, `collided`)
+ *   edge_index [2, E_total] i64 caller's edges, node ids LOCAL to the problem's cat(path, free, collided)
+ *                               (smoother.py:238-241 passes the path chain + self loops)            (`edge_index`)
+ *   scale    ModelSmoother.scale (model_smoother.py:55,118-120,142);  loop: model_smoother.py:104 (model_smooth uses 1)
+ *   path_out [P_total, c] f32   new path; rows 0 and P_g-1 of each problem keep their input value (model_smoother.py:139)
+ * The caller's `path` is not modified (the reference divides first, model_smoother.py:118). */
+int gmp_smoother_forward(gmp_handle* h, int64_t n_problems, const float* path, const float* samples,
+                         const int64_t* edge_index, int64_t edge_row_stride, const int32_t* path_ptr_h,
+                         const int32_t* sample_ptr_h, const int32_t* n_free_h, const int32_t* edge_ptr_h, float scale,
+                         int loop, float* path_out, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- per-problem result rows: the final reduction of eval_gnn (eval_gnn.py:120-134) ----------- */
 /* One row of 4 floats per graph: (first_problem_id + g, E_g, #edges with edge_free != 0, max edge logit).
  * edge_ptr is a DEVICE array [B+1]; edge_free is nullable.  These rows are the only payload of the multi-GPU

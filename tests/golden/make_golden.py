@@ -220,6 +220,31 @@ def main():
         print("smoother", tag, newp.shape)
     np.savez_compressed(os.path.join(HERE, "smoother.npz"), **sm)
 
+    # ---------------------------------------------------------------- arm problem subsets (data of maze_files/kukas_*.pkl)
+    # obstacles + the PyBullet-verified free states the dataset ships (start, goal, solution waypoints): a sanity band
+    # for the arm model (PyBullet itself cannot run here: arm parity is unpinned).
+    import pickle
+    arm = {}
+    for tag, fn in (("kuka7", "kukas_7_3000.pkl"), ("kuka14", "kukas_14_3000.pkl"), ("kuka13", "kukas_13_3000.pkl")):
+        with open(os.path.join(REF, "maze_files", fn), "rb") as f:
+            pr = pickle.load(f)[:48]
+        boxes, ptr, known, known_p, ea, eb, ep = [], [0], [], [], [], [], []
+        for i, (obs, st, go, path) in enumerate(pr):
+            for h, b in obs:
+                boxes.append(np.concatenate([h, b]))
+            ptr.append(len(boxes))
+            for q in [st, go] + list(path):
+                known.append(np.asarray(q, np.float64)); known_p.append(i)
+            path = np.asarray(path, np.float64)
+            for u, w in zip(path[:-1], path[1:]):
+                ea.append(u); eb.append(w); ep.append(i)
+        arm.update({tag + "_boxes": np.array(boxes), tag + "_box_ptr": np.array(ptr, np.int32),
+                    tag + "_known_free": np.array(known), tag + "_known_free_problem": np.array(known_p, np.int32),
+                    tag + "_path_a": np.array(ea), tag + "_path_b": np.array(eb), tag + "_path_problem": np.array(ep, np.int32),
+                    tag + "_start": np.array([p[1] for p in pr]), tag + "_goal": np.array([p[2] for p in pr])})
+        print("arm problems", tag, len(boxes), "boxes,", len(known), "known-free states")
+    np.savez_compressed(os.path.join(HERE, "arm_problems.npz"), **arm)
+
     # ---------------------------------------------------------------- end-to-end explore() golden: BASELINE config C1
     # reference eval_gnn.explore(batch=100, t_max=100, k=10, smoother='none') on real maze problems
     # (main.ipynb cell 8 / BASELINE.json configs[0]) with the reference MazeEnv and reference model.

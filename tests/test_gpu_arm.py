@@ -1,0 +1,104 @@
+"""GPU: arm collision kernels vs the C oracle -- bit-exact booleans and check counts (model-level parity; PyBullet
+parity is unpinned)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+MODELS = [("kuka7", 0, 7), ("kuka14", 1, 14), ("kuka13", 2, 13)]
+
+
+@pytest.fixture(scope="module")
+def probs():
+    return np.load(os.path.join(G, "arm_problems.npz"))
+
+
+@pytest.mark.parametrize("tag,model,dof", MODELS)
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_state_and_edge_vs_oracle(cuda_device, probs, tag, model, dof, dt):
+    from gnn_motion_planning_b200 import collision
+    from oracle import arm as o_arm
+    d, lo, hi = collision.arm_model_info(model)
+    assert d == dof
+    olo, ohi = o_arm.limits(model)
+    assert np.array_equal(lo, olo) and np.array_equal(hi, ohi)
+    boxes, ptr = probs[tag + "_boxes"], probs[tag + "_box_ptr"]
+    P = len(ptr) - 1
+    rng = np.random.default_rng(3)
+    n = 60000
+    q = rng.uniform(lo * 1.01, hi * 1.01, (n, dof)).astype(dt)        # a few out of limits
+    prob = rng.integers(0, P, n).astype(np.int32)
+    bd, pd = torch.from_numpy(boxes).to(cuda_device), torch.from_numpy(ptr).to(cuda_device)
+    free, counted = collision.arm_state_fp(model, torch.from_numpy(q).to(cuda_device), bd, pd, torch.from_numpy(prob).to(cuda_device),
+                                           want_counted=True)
+    of, oc = o_arm.state_fp(model, q, boxes, ptr, prob)
+    assert np.array_equal(free.cpu().numpy(), of) and np.array_equal(counted.cpu().numpy(), oc)
+    assert 0.2 < of.mean() < 0.95
+    m = 20000
+    a = rng.uniform(lo, hi, (m, dof)).astype(dt)
+    b = np.clip(a + rng.normal(0, 0.6, (m, dof)), lo * 1.005, hi * 1.005).astype(dt)
+    free, checks = collision.arm_edge_fp(model, torch.from_numpy(a).to(cuda_device), torch.from_numpy(b).to(cuda_device), bd, pd,
+                                         torch.from_numpy(prob[:m]).to(cuda_device), rrt_eps=0.5, want_checks=True)
+    of, oc = o_arm.edge_fp(model, a, b, boxes, ptr, prob[:m], rrt_eps=0.5)
+    assert np.array_equal(free.cpu().numpy(), of)
+    assert np.array_equal(checks.cpu().numpy(), oc)
+    assert 0.05 < of.mean() < 0.95
+
+
+def test_edge_graph_matches_explicit(cuda_device, probs):
+    from gnn_motion_planning_b200 import collision
+    boxes, ptr = probs["kuka7_boxes"], probs["kuka7_box_ptr"]
+    _, lo, hi = collision.arm_model_info(0)
+    rng = np.random.default_rng(5)
+    B, n = 4, 150
+    v = rng.uniform(lo, hi, (B * n, 7)).astype(np.float32)
+    es = [rng.integers(0, n, (2, 500 + 7 * g)) for g in range(B)]
+    edge_ptr = np.cumsum([0] + [e.shape[1] for e in es]).astype(np.int32)
+    node_ptr = (np.arange(B + 1) * n).astype(np.int32)
+    ei = np.concatenate(es, 1).astype(np.int64)
+    dev = cuda_device
+    bd, pd = torch.from_numpy(boxes).to(dev), torch.from_numpy(ptr).to(dev)
+    pg = torch.tensor([3, 0, 7, 7], dtype=torch.int32, device=dev)
+    free, checks = collision.arm_edge_fp_graph(0, torch.from_numpy(v).to(dev), torch.from_numpy(ei).to(dev), torch.from_numpy(node_ptr).to(dev),
+                                               torch.from_numpy(edge_ptr).to(dev), bd, pd, int(edge_ptr[-1]), rrt_eps=0.5,
+                                               problem_of_graph=pg, want_checks=True)
+    gid = np.repeat(np.arange(B), np.diff(edge_ptr))
+    a, b = v[ei[0] + node_ptr[gid]], v[ei[1] + node_ptr[gid]]
+    f2, c2 = collision.arm_edge_fp(0, torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev), bd, pd,
+                                   torch.from_numpy(pg.cpu().numpy()[gid]).to(dev), rrt_eps=0.5, want_checks=True)
+    assert torch.equal(free, f2) and torch.equal(checks, c2)
+
+
+def test_kuka_env_protocol(cuda_device, probs):
+    """Drop-in env: scalar _state_fp/_edge_fp + collision_check_count agree with the oracle; sampler keeps the RNG stream."""
+    from gnn_motion_planning_b200.environment import Kuka2Env, KukaEnv
+    from oracle import arm as o_arm
+    for tag, cls, model in (("kuka7", KukaEnv, 0), ("kuka14", Kuka2Env, 1)):
+        boxes, ptr = probs[tag + "_boxes"], probs[tag + "_box_ptr"]
+        problems = []
+        for i in range(len(ptr) - 1):
+            obs = [(boxes[j, :3], boxes[j, 3:]) for j in range(ptr[i], ptr[i + 1])]
+            problems.append((obs, probs[tag + "_start"][i], probs[tag + "_goal"][i], []))
+        env = cls(problems=problems)
+        assert str(env) == tag and env.config_dim == {"kuka7": 7, "kuka14": 14}[tag] and env.RRT_EPS == 0.5
+        env.init_new_problem(2)
+        np.random.seed(4)
+        free, coll = env.sample_n_points(30, need_negative=True)
+        assert len(free) == 30 and env.collision_check_count == len(free) + len(coll)
+        np.random.seed(4)     # reference loop: one draw per check, stop at the 30th free sample
+        pr = np.array(env.pose_range)
+        ref_free = []
+        while len(ref_free) < 30:
+            s = np.random.uniform(pr[:, 0], pr[:, 1], size=(1, env.config_dim)).reshape(-1)
+            if o_arm.state_fp(model, s[None], boxes, ptr, np.array([2], np.int32))[0][0]:
+                ref_free.append(s)
+        assert np.array_equal(np.array(free), np.array(ref_free))
+        c0 = env.collision_check_count
+        a, b = free[0].astype(np.float32), free[1].astype(np.float32)
+        got = env._edge_fp(a, b)
+        of, oc = o_arm.edge_fp(model, a[None], b[None], boxes, ptr, np.array([2], np.int32), rrt_eps=0.5)
+        assert got == bool(of[0]) and env.collision_check_count - c0 == oc[0]
+        assert env._state_fp(np.asarray(env.init_state)) in (True, False)

@@ -46,9 +46,27 @@ def make_problem(wl, g):
         occ = np.argwhere(maps[g % len(maps)] == 1)
         obs = (occ / 15.0 - 0.5).astype(np.float32)
     else:
-        nb = 2 + g % 8
-        obs = np.concatenate([rng.uniform(0.1, 0.3, (nb, 3)), rng.uniform(-0.8, 0.8, (nb, 3))], 1).astype(np.float32)
+        ap = _arm_problems()
+        tag = wl["env"]
+        ptr = ap[tag + "_box_ptr"]
+        pi = g % (len(ptr) - 1)
+        obs = ap[tag + "_boxes"][ptr[pi]:ptr[pi + 1]].astype(np.float32)      # [O,6] = (halfExtents, basePosition)
+        lo, hi = ARM_LIMITS[tag]
+        v = rng.uniform(lo, hi, (wl["n"], wl["c"])).astype(np.float32)
     return v, obs
+
+
+_AP = {}
+ARM_LIMITS = {"kuka7": (np.array([-2.96705972839, -2.09439510239, -2.96705972839, -2.09439510239, -2.96705972839, -2.09439510239, -3.05432619099]),
+                        np.array([2.96705972839, 2.09439510239, 2.96705972839, 2.09439510239, 2.96705972839, 2.09439510239, 3.05432619099]))}
+ARM_LIMITS["kuka14"] = (np.tile(ARM_LIMITS["kuka7"][0], 2), np.tile(ARM_LIMITS["kuka7"][1], 2))
+ARM_MODEL = {"kuka7": 0, "kuka14": 1}
+
+
+def _arm_problems():
+    if "d" not in _AP:
+        _AP["d"] = np.load(os.path.join(G, "arm_problems.npz"))
+    return _AP["d"]
 
 
 def ref_oplist_flops(n, e_cnt, o, c, e, s, loop=5):
@@ -127,6 +145,13 @@ def cpu_graphs_per_sec(wl, graph_ids, threads):
                                     torch.from_numpy(obs), loop=5, dense=False)
         if wl["env"] == "maze2":
             o_maze.edge_fp(v[ei[0]], v[ei[1]], maps, np.full(ei.shape[1], g % len(maps), np.int32))
+        else:
+            from oracle import arm as o_arm
+            ap = _arm_problems()
+            tag = wl["env"]
+            ptr = ap[tag + "_box_ptr"]
+            o_arm.edge_fp(ARM_MODEL[tag], v[ei[0]], v[ei[1]], ap[tag + "_boxes"], ptr,
+                          np.full(ei.shape[1], g % (len(ptr) - 1), np.int32), rrt_eps=0.5)
         n_edges += ei.shape[1]
     dt = time.perf_counter() - t0
     return len(graph_ids) / dt, dt, n_edges
@@ -219,6 +244,11 @@ def main():
     maps_h = torch.from_numpy(np.ascontiguousarray(maps_np)).pin_memory()
     prob_h = torch.from_numpy(((rank * B + np.arange(B)) % len(maps_np)).astype(np.int32)).pin_memory()
     is_maze = wl["env"] == "maze2"
+    if not is_maze:
+        ap = _arm_problems()
+        boxes_d = torch.from_numpy(ap[wl["env"] + "_boxes"]).to(dev)
+        box_ptr_d = torch.from_numpy(ap[wl["env"] + "_box_ptr"]).to(dev)
+        prob_h = torch.from_numpy(((rank * B + np.arange(B)) % (len(ap[wl["env"] + "_box_ptr"]) - 1)).astype(np.int32)).pin_memory()
 
     model = EncoderProcessDecoder(workspace_size=wl["ws"], config_size=c, embed_size=wl["e"], obs_size=wl["s"]).to(dev)
     model.load_state_dict(torch.load(os.path.join(G, "weights", wl["weights"]), map_location="cpu"))
@@ -252,9 +282,12 @@ def main():
         if is_maze:
             collision.maze_edge_fp_graph(v, ei, node_ptr_d, edge_ptr_d, maps, et, problem_of_graph=prob, want_checks=True,
                                          free_out=free_buf, checks_out=checks_buf)
+        else:
+            collision.arm_edge_fp_graph(ARM_MODEL[wl["env"]], v, ei, node_ptr_d, edge_ptr_d, boxes_d, box_ptr_d, et, rrt_eps=0.5,
+                                        problem_of_graph=prob, want_checks=True, free_out=free_buf, checks_out=checks_buf)
         e3.record()
         # per-problem result rows: (problem id, E_g, #collision-free edges, best logit) -> the only collective
-        rows = collision.result_rows(logits, free_buf if is_maze else None, edge_ptr_d, rank * B, out=rows_buf)
+        rows = collision.result_rows(logits, free_buf, edge_ptr_d, rank * B, out=rows_buf)
         if world > 1:
             dist.all_gather_into_tensor(gather_buf.view(world * B, 4), rows)
         state.update(et=et, edge_ptr=edge_ptr, rows=rows, ei=ei)
@@ -292,8 +325,7 @@ def main():
     ms_step = timed_region(lambda: step(v_d, goal_d, obs_d, maps_d, prob_d, timed=True), args.steps)
     clocks = sampler.stop() if sampler else None
     et = state["et"]
-    n_free_edges = float(state["rows"][:, 2].sum()) if is_maze else None
-    checks_total = int(checks_buf[:et].sum()) if is_maze else None
+    checks_total = int(checks_buf[:et].sum())
 
     # ---- end to end: host (pinned) buffers in, host buffers out, copies inside the timed region
     out_logits_h = torch.empty(cap, dtype=torch.float32).pin_memory()
@@ -351,8 +383,9 @@ def main():
         "edges_per_graph": e_mean, "obstacles_per_graph": o_mean,
         "phases_ms_per_step": {k_: v_ / K for k_, v_ in sorted(phase_ms.items())},
         "explorer_forward_graphs_per_sec": B * world / (phase_ms["explorer_forward"] / K / 1e3),
-        "collision_checks_per_sec": (et * world / (phase_ms["collision"] / K / 1e3)) if is_maze else None,
-        "collision_lookups_per_edge": (checks_total / et) if is_maze else None,
+        "collision_checks_per_sec": et * world / (phase_ms["collision"] / K / 1e3),
+        "collision_state_checks_per_edge": checks_total / et,
+        "collision_free_edge_fraction": float(state["rows"][:, 2].sum()) / et,
         "knn_graphs_per_sec": B * world / (phase_ms["knn_graph"] / K / 1e3),
         "forward_tflops_ref_oplist": fwd_flops / (phase_ms["explorer_forward"] / K / 1e3) / 1e12,
         "roofline": {"kernel": "edge_feature_kernel<%d,%d>" % (c, wl["e"]), "bound": "tensor", "achieved": ef_tflops, "peak": peak_tf,
@@ -365,9 +398,9 @@ def main():
                                 "ms_per_launch": msg_ms},
         "e2e": {"value": B * world / (ms_e2e / 1000.0), "unit": "graphs/s", "h2d_bytes_per_step": io["h2d"], "d2h_bytes_per_step": io["d2h"],
                 "ms_per_step": ms_e2e},
-        "gpu_launches": K * (5 + 3 + 1 + 1 + 1 + 1 + 6 + 5 + 1 + 1 + (1 if is_maze else 0)),
+        "gpu_launches": K * (5 + 3 + 1 + 1 + 1 + 1 + 6 + 5 + 1 + 1 + 1),
         "gpu_launches_note": "per step: knn 5 (select,row_count,row_scan,graph_scan,emit) + csr 3 + goal_index + obstacle + node_pre + "
-                             "edge_feature + node_loop x6 + edge_msg x5 + policy + maze_edge_graph + result_rows; memsets/copies not counted",
+                             "edge_feature + node_loop x6 + edge_msg x5 + policy + {maze,arm}_edge_graph + result_rows; memsets/copies not counted",
         "clocks": clocks,
     }
     if world == 1 and not args.no_cpu_baseline:

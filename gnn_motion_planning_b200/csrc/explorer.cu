@@ -43,17 +43,20 @@ constexpr float kLnEps = 1e-6f;  // model.py:163,189
 // ------------------------------------------------------------------------------------------------
 // shared-memory carve-up of a row-tile CTA
 // ------------------------------------------------------------------------------------------------
-template <int E>
+template <int E, bool WITH_S = true>
 struct Smem {
   using Cf = RowCfg<E>;
   static constexpr int kBuf = E * Cf::RP;                 // one feature-major activation buffer
   static constexpr int kWB = (E > 64 ? E : 64) * E + 4 * E;  // one weight stage: matrix (K <= max(E, 4c <= 64)) + up to 4 vectors
   static constexpr int kOB = 2 * E * Cf::OT;              // one obstacle tile: Mt [E][OT] | V [OT][E]
-  static constexpr int kFloats = 2 * kBuf + kWB + kOB;
+  static constexpr int kFloats = (WITH_S ? 2 : 1) * kBuf + kWB + kOB;
   static constexpr size_t kBytes = (size_t)kFloats * sizeof(float) + Cf::R * sizeof(int);
   float* X; float* S; float* WB; float* OB; int* IDX;
+  // the hot per-edge kernels run without the scratch buffer S (chained through registers / X reused in place):
+  // half the shared memory per CTA, twice the resident warps
   __device__ explicit Smem(float* base) {
-    X = base; S = X + kBuf; WB = S + kBuf; OB = WB + kWB; IDX = reinterpret_cast<int*>(OB + kOB);
+    X = base; S = WITH_S ? X + kBuf : nullptr; WB = X + (WITH_S ? 2 : 1) * kBuf; OB = WB + kWB;
+    IDX = reinterpret_cast<int*>(OB + kOB);
   }
 };
 
@@ -73,13 +76,12 @@ __device__ __forceinline__ void acc_add_vec(float (&acc)[TM][N], const float* __
 // one Block on the map rows of this tile: X <- map_feed(attention(X, obstacles))   (model.py:212-215)
 // `tab` points at this graph's first obstacle tile for this block; tiles are 2*E*OT floats apart.
 // ------------------------------------------------------------------------------------------------
-template <int E>
-__device__ __forceinline__ void map_block(const Smem<E>& sm, const float* __restrict__ W, const BlockW bw,
+template <int E, typename SM>
+__device__ __forceinline__ void map_block(const SM& sm, const float* __restrict__ W, const BlockW bw,
                                           const float* __restrict__ tab, int n_obs) {
   using Cf = RowCfg<E>;
   constexpr int TM = Cf::TM, RP = Cf::RP, OT = Cf::OT;
   float* xcol = sm.X + threadIdx.x;
-  float* scol = sm.S + threadIdx.x;
   float acc[TM][E];
   float m[TM], l[TM];
 
@@ -127,8 +129,7 @@ __device__ __forceinline__ void map_block(const Smem<E>& sm, const float* __rest
       l[r] = lsum;
       m[r] = mnew;
     }
-    acc_store<TM, OT, RP>(s, scol);
-    gemm_smem<OT, E, TM, RP>(acc, scol, sm.OB + E * OT);
+    gemm_reg<OT, E, TM>(acc, s, sm.OB + E * OT);   // P.V with the probabilities still in registers
   }
   // softmax normalisation, residual, attention.layer_norm                   (model.py:181)
 #pragma unroll
@@ -140,26 +141,30 @@ __device__ __forceinline__ void map_block(const Smem<E>& sm, const float* __rest
   acc_layernorm(acc, sm.WB + E * E, sm.WB + E * E + E, kLnEps);
   acc_store<TM, E, RP>(acc, xcol);
 
-  // map_feed                                                                (model.py:193-201)
+  // map_feed: the residual stays in registers, the hidden layer overwrites X in place   (model.py:193-201)
+  float h[TM][E];
   stage_load(sm.WB, W + bw.W1t, E * E + E);
-  acc_zero(acc);
-  gemm_smem<E, E, TM, RP>(acc, xcol, sm.WB);
-  acc_add_vec(acc, sm.WB + E * E);
-  acc_relu(acc);
-  acc_store<TM, E, RP>(acc, scol);
+  acc_zero(h);
+  gemm_smem<E, E, TM, RP>(h, xcol, sm.WB);
+  acc_add_vec(h, sm.WB + E * E);
+  acc_relu(h);
+  acc_store<TM, E, RP>(h, xcol);
   stage_load(sm.WB, W + bw.W2t, E * E + 3 * E);
-  acc_zero(acc);
-  gemm_smem<E, E, TM, RP>(acc, scol, sm.WB);
-  acc_add_vec(acc, sm.WB + E * E);
-  acc_add_col<TM, E, RP>(acc, xcol);
-  acc_layernorm(acc, sm.WB + E * E + E, sm.WB + E * E + 2 * E, kLnEps);
-  acc_store<TM, E, RP>(acc, xcol);
+  acc_zero(h);
+  gemm_smem<E, E, TM, RP>(h, xcol, sm.WB);
+  acc_add_vec(h, sm.WB + E * E);
+#pragma unroll
+  for (int r = 0; r < TM; ++r)
+#pragma unroll
+    for (int n = 0; n < E; ++n) h[r][n] += acc[r][n];
+  acc_layernorm(h, sm.WB + E * E + E, sm.WB + E * E + 2 * E, kLnEps);
+  acc_store<TM, E, RP>(h, xcol);
 }
 
 // two-layer encoder Seq(Lin, ReLU, Lin) with the first layer's inputs in registers: result -> `out` column.
 // `hid` is the scratch column for the hidden layer (may equal `out`).
-template <int K, int E>
-__device__ __forceinline__ void encoder_mlp(const Smem<E>& sm, const float* __restrict__ W, int off0, int off2,
+template <int K, int E, typename SM>
+__device__ __forceinline__ void encoder_mlp(const SM& sm, const float* __restrict__ W, int off0, int off2,
                                             const float (&in)[RowCfg<E>::TM][K], float* hid, float* out) {
   using Cf = RowCfg<E>;
   constexpr int TM = Cf::TM, RP = Cf::RP;
@@ -475,7 +480,7 @@ __global__ void __launch_bounds__(kRtThreads) node_pre_kernel(ExplorerW w, const
 // grid: one CTA per (graph, edge tile)
 // ------------------------------------------------------------------------------------------------
 template <int C, int E>
-__global__ void __launch_bounds__(kRtThreads, 2) edge_feature_kernel(
+__global__ void __launch_bounds__(kRtThreads, 3) edge_feature_kernel(
     ExplorerW w, const float* __restrict__ W, const float* __restrict__ v, const int32_t* __restrict__ csr_src,
     const int32_t* __restrict__ csr_dst, const int32_t* __restrict__ edge_ptr, const int32_t* __restrict__ tile_ptr, int n_graphs,
     const int32_t* __restrict__ obs_ptr, const int32_t* __restrict__ obs_tile_ptr, const float* __restrict__ tables,
@@ -483,9 +488,8 @@ __global__ void __launch_bounds__(kRtThreads, 2) edge_feature_kernel(
   using Cf = RowCfg<E>;
   constexpr int TM = Cf::TM, R = Cf::R, RP = Cf::RP, OT = Cf::OT;
   extern __shared__ __align__(16) float smem_raw[];
-  Smem<E> sm(smem_raw);
+  Smem<E, false> sm(smem_raw);
   float* xcol = sm.X + threadIdx.x;
-  float* scol = sm.S + threadIdx.x;
   const int g = find_segment(tile_ptr, n_graphs, blockIdx.x);
   const int slot0 = edge_ptr[g] + (blockIdx.x - tile_ptr[g]) * R;
   const int slot1 = edge_ptr[g + 1];
@@ -512,7 +516,7 @@ __global__ void __launch_bounds__(kRtThreads, 2) edge_feature_kernel(
   {
     float in[TM][2 * C];
     gather_in(in);
-    encoder_mlp<2 * C, E>(sm, W, w.ef0, w.ef2, in, scol, xcol);              // edge_free_code, model.py:123
+    encoder_mlp<2 * C, E>(sm, W, w.ef0, w.ef2, in, xcol, xcol);              // edge_free_code, model.py:123 (hidden in place)
   }
   if (use_obstacles) {
     const int n_obs = obs_ptr[g + 1] - obs_ptr[g];
@@ -521,22 +525,7 @@ __global__ void __launch_bounds__(kRtThreads, 2) edge_feature_kernel(
       map_block<E>(sm, W, w.edge_blk[blk], tab, n_obs);                      // model.py:130
     }
   }
-  {
-    float in[TM][2 * C];
-    gather_in(in);
-    encoder_mlp<2 * C, E>(sm, W, w.ec0, w.ec2, in, scol, scol);              // edge_code -> S, model.py:120
-  }
   float acc[TM][E];
-  // P = W4 ef + W5 ec + b  : loop-invariant part of lin_0[0]                (model.py:39,142)
-  stage_load(sm.WB, W + w.l0_ef, E * E);
-  acc_zero(acc);
-  gemm_smem<E, E, TM, RP>(acc, xcol, sm.WB);
-  stage_load(sm.WB, W + w.l0_ec, E * E + E);
-  gemm_smem<E, E, TM, RP>(acc, scol, sm.WB);
-  acc_add_vec(acc, sm.WB + E * E);
-#pragma unroll
-  for (int r = 0; r < TM; ++r)
-    if (valid[r]) acc_store_global<TM, E>(acc, r, P + (size_t)slot[r] * E);
   // Q = Wc ef + b : loop-invariant part of policy[0]                        (model.py:145-146)
   stage_load(sm.WB, W + w.p0_ef, E * E + E);
   acc_zero(acc);
@@ -545,6 +534,34 @@ __global__ void __launch_bounds__(kRtThreads, 2) edge_feature_kernel(
 #pragma unroll
   for (int r = 0; r < TM; ++r)
     if (valid[r]) acc_store_global<TM, E>(acc, r, Q + (size_t)slot[r] * E);
+  // P = W4 ef + W5 ec + b  : loop-invariant part of lin_0[0]                (model.py:39,142)
+  // W4 ef is parked in X (ef is dead after this), edge_code is chained through registers.
+  stage_load(sm.WB, W + w.l0_ef, E * E);
+  acc_zero(acc);
+  gemm_smem<E, E, TM, RP>(acc, xcol, sm.WB);
+  acc_store<TM, E, RP>(acc, xcol);
+  {
+    float in[TM][2 * C];
+    gather_in(in);
+    stage_load(sm.WB, W + w.ec0, 2 * C * E + E);                             // edge_code, model.py:120
+    acc_zero(acc);
+    gemm_reg<2 * C, E, TM>(acc, in, sm.WB);
+    acc_add_vec(acc, sm.WB + 2 * C * E);
+    acc_relu(acc);
+  }
+  float ec[TM][E];
+  stage_load(sm.WB, W + w.ec2, E * E + E);
+  acc_zero(ec);
+  gemm_reg<E, E, TM>(ec, acc, sm.WB);
+  acc_add_vec(ec, sm.WB + E * E);
+  stage_load(sm.WB, W + w.l0_ec, E * E + E);
+  acc_zero(acc);
+  gemm_reg<E, E, TM>(acc, ec, sm.WB);
+  acc_add_vec(acc, sm.WB + E * E);
+  acc_add_col<TM, E, RP>(acc, xcol);
+#pragma unroll
+  for (int r = 0; r < TM; ++r)
+    if (valid[r]) acc_store_global<TM, E>(acc, r, P + (size_t)slot[r] * E);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -659,8 +676,8 @@ __global__ void __launch_bounds__(kRtThreads) node_loop_kernel(ExplorerW w, cons
 }
 
 // hidden = relu(A[src] + B[dst] + PQ[slot]) -> this thread's X columns
-template <int E>
-__device__ __forceinline__ void edge_hidden(const Smem<E>& sm, const int (&slot)[RowCfg<E>::TM], const bool (&valid)[RowCfg<E>::TM],
+template <int E, typename SM>
+__device__ __forceinline__ void edge_hidden(const SM& sm, const int (&slot)[RowCfg<E>::TM], const bool (&valid)[RowCfg<E>::TM],
                                             const int32_t* __restrict__ csr_src, const int32_t* __restrict__ csr_dst,
                                             const float* __restrict__ A, const float* __restrict__ B,
                                             const float* __restrict__ PQ) {
@@ -696,7 +713,7 @@ __device__ __forceinline__ void edge_hidden(const Smem<E>& sm, const int (&slot)
 // messages + max aggregation for one round; rows = CSR slots, flat over the batch   (model.py:33,38-41)
 // ------------------------------------------------------------------------------------------------
 template <int E>
-__global__ void __launch_bounds__(kRtThreads, 2) edge_msg_kernel(ExplorerW w, const float* __restrict__ W, int n_slots,
+__global__ void __launch_bounds__(kRtThreads, 4) edge_msg_kernel(ExplorerW w, const float* __restrict__ W, int n_slots,
                                                                  const int32_t* __restrict__ csr_src,
                                                                  const int32_t* __restrict__ csr_dst, const float* __restrict__ A,
                                                                  const float* __restrict__ B, const float* __restrict__ P,
@@ -704,7 +721,7 @@ __global__ void __launch_bounds__(kRtThreads, 2) edge_msg_kernel(ExplorerW w, co
   using Cf = RowCfg<E>;
   constexpr int TM = Cf::TM, R = Cf::R, RP = Cf::RP;
   extern __shared__ __align__(16) float smem_raw[];
-  Smem<E> sm(smem_raw);
+  Smem<E, false> sm(smem_raw);
   int slot[TM];
   bool valid[TM];
 #pragma unroll
@@ -718,7 +735,7 @@ __global__ void __launch_bounds__(kRtThreads, 2) edge_msg_kernel(ExplorerW w, co
   acc_zero(acc);
   gemm_smem<E, E, TM, RP>(acc, sm.X + threadIdx.x, sm.WB);
   acc_add_vec(acc, sm.WB + E * E);
-  acc_store<TM, E, RP>(acc, sm.S + threadIdx.x);
+  acc_store<TM, E, RP>(acc, sm.X + threadIdx.x);   // in place: a thread only ever read its own columns of X
   __syncthreads();
   // segmented max: thread = (feature n, row group); rows of a group are walked in CSR order, so a
   // target's rows are consecutive; one RED per (segment, feature), 128 B coalesced across the warp.
@@ -735,7 +752,7 @@ __global__ void __launch_bounds__(kRtThreads, 2) edge_msg_kernel(ExplorerW w, co
       cur = d;
       run = -INFINITY;
     }
-    run = fmaxf(run, sm.S[n * RP + r0 + i]);
+    run = fmaxf(run, sm.X[n * RP + r0 + i]);
   }
   if (cur >= 0) atomic_max_f32(AGG + (size_t)cur * E + n, run);
 }
@@ -744,7 +761,7 @@ __global__ void __launch_bounds__(kRtThreads, 2) edge_msg_kernel(ExplorerW w, co
 // policy head; rows = CSR slots, flat over the batch                              (model.py:145-150)
 // ------------------------------------------------------------------------------------------------
 template <int E>
-__global__ void __launch_bounds__(kRtThreads, 2) policy_kernel(ExplorerW w, const float* __restrict__ W, int n_slots,
+__global__ void __launch_bounds__(kRtThreads, 4) policy_kernel(ExplorerW w, const float* __restrict__ W, int n_slots,
                                                                const int32_t* __restrict__ csr_src,
                                                                const int32_t* __restrict__ csr_dst,
                                                                const int32_t* __restrict__ csr_eid, const float* __restrict__ G,
@@ -756,7 +773,7 @@ __global__ void __launch_bounds__(kRtThreads, 2) policy_kernel(ExplorerW w, cons
   using Cf = RowCfg<E>;
   constexpr int TM = Cf::TM, R = Cf::R, RP = Cf::RP;
   extern __shared__ __align__(16) float smem_raw[];
-  Smem<E> sm(smem_raw);
+  Smem<E, false> sm(smem_raw);
   int slot[TM];
   bool valid[TM];
 #pragma unroll
@@ -1057,15 +1074,16 @@ int run_forward(gmp_handle* h, int64_t B, const float* v, const int64_t* edge_in
   GMP_CUDA(cudaMemcpyAsync(ws.dense_off, dense_off.data(), (B + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
   // (pageable sources: cudaMemcpyAsync has staged them before returning, so the vectors may die)
 
-  const size_t smem = Smem<E>::kBytes;
+  const size_t smem = Smem<E, true>::kBytes;     // node / obstacle kernels (two activation buffers)
+  const size_t smem1 = Smem<E, false>::kBytes;   // per-edge kernels (one activation buffer)
   static bool attr_done = false;
   if (!attr_done) {
     GMP_CUDA(cudaFuncSetAttribute(obstacle_kernel<S, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     GMP_CUDA(cudaFuncSetAttribute(node_pre_kernel<C, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GMP_CUDA(cudaFuncSetAttribute(edge_feature_kernel<C, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GMP_CUDA(cudaFuncSetAttribute(edge_feature_kernel<C, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
     GMP_CUDA(cudaFuncSetAttribute(node_loop_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GMP_CUDA(cudaFuncSetAttribute(edge_msg_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GMP_CUDA(cudaFuncSetAttribute(policy_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GMP_CUDA(cudaFuncSetAttribute(edge_msg_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+    GMP_CUDA(cudaFuncSetAttribute(policy_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
     attr_done = true;
   }
   const float* W = m.d_weights;
@@ -1112,7 +1130,7 @@ int run_forward(gmp_handle* h, int64_t B, const float* v, const int64_t* edge_in
   tl.end(st);
   tl.begin(kPhEdgeFeature, st);
   if (tile_e[B] > 0) {
-    edge_feature_kernel<C, E><<<tile_e[B], kRtThreads, smem, st>>>(m.w, W, v, ws.csr_src, ws.csr_dst, ws.edge_ptr, ws.tile_ptr_e,
+    edge_feature_kernel<C, E><<<tile_e[B], kRtThreads, smem1, st>>>(m.w, W, v, ws.csr_src, ws.csr_dst, ws.edge_ptr, ws.tile_ptr_e,
                                                                   (int)B, ws.obs_ptr, ws.obs_tile_ptr, ws.tables, table_stride,
                                                                   use_obstacles, ws.P, ws.Q);
     GMP_LAUNCH_CHECK();
@@ -1129,7 +1147,7 @@ int run_forward(gmp_handle* h, int64_t B, const float* v, const int64_t* edge_in
     }
     if (it < loop && slot_tiles > 0) {
       tl.begin(kPhEdgeMsg, st);
-      edge_msg_kernel<E><<<slot_tiles, kRtThreads, smem, st>>>(m.w, W, (int)Et, ws.csr_src, ws.csr_dst, ws.A, ws.B, ws.P, ws.AGG);
+      edge_msg_kernel<E><<<slot_tiles, kRtThreads, smem1, st>>>(m.w, W, (int)Et, ws.csr_src, ws.csr_dst, ws.A, ws.B, ws.P, ws.AGG);
       GMP_LAUNCH_CHECK();
       tl.end(st);
     }
@@ -1137,7 +1155,7 @@ int run_forward(gmp_handle* h, int64_t B, const float* v, const int64_t* edge_in
   tl.begin(kPhPolicy, st);
   if (dense && dense_off[B] > 0) GMP_CUDA(cudaMemsetAsync(dense, 0, dense_off[B] * sizeof(float), st));
   if (slot_tiles > 0) {
-    policy_kernel<E><<<slot_tiles, kRtThreads, smem, st>>>(m.w, W, (int)Et, ws.csr_src, ws.csr_dst, ws.csr_eid, ws.A, ws.B, ws.Q,
+    policy_kernel<E><<<slot_tiles, kRtThreads, smem1, st>>>(m.w, W, (int)Et, ws.csr_src, ws.csr_dst, ws.csr_eid, ws.A, ws.B, ws.Q,
                                                           ws.edge_ptr, ws.node_ptr, ws.dense_off, (int)B, logits, dense);
     GMP_LAUNCH_CHECK();
   }

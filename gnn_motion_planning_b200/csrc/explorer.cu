@@ -50,13 +50,14 @@ struct Smem {
   static constexpr int kWB = (E > 64 ? E : 64) * E + 4 * E;  // one weight stage: matrix (K <= max(E, 4c <= 64)) + up to 4 vectors
   static constexpr int kOB = 2 * E * Cf::OT;              // one obstacle tile: Mt [E][OT] | V [OT][E]
   static constexpr int kFloats = (WITH_S ? 2 : 1) * kBuf + kWB + kOB;
-  static constexpr size_t kBytes = (size_t)kFloats * sizeof(float) + Cf::R * sizeof(int);
-  float* X; float* S; float* WB; float* OB; int* IDX;
+  static constexpr size_t kBytes = (size_t)kFloats * sizeof(float) + 2 * Cf::R * sizeof(int);
+  float* X; float* S; float* WB; float* OB; int* IDX; int* SRC;
   // the hot per-edge kernels run without the scratch buffer S (chained through registers / X reused in place):
   // half the shared memory per CTA, twice the resident warps
   __device__ explicit Smem(float* base) {
     X = base; S = WITH_S ? X + kBuf : nullptr; WB = X + (WITH_S ? 2 : 1) * kBuf; OB = WB + kWB;
     IDX = reinterpret_cast<int*>(OB + kOB);
+    SRC = IDX + Cf::R;
   }
 };
 
@@ -675,37 +676,43 @@ __global__ void __launch_bounds__(kRtThreads) node_loop_kernel(ExplorerW w, cons
     if (valid[r]) acc_store_global<TM, E>(acc, r, B + (size_t)row[r] * E);
 }
 
-// hidden = relu(A[src] + B[dst] + PQ[slot]) -> this thread's X columns
+// hidden = relu(A[src] + B[dst] + PQ[slot]) for the R rows of this tile -> X (feature-major), IDX[row] = dst.
+// The tile's CSR indices are staged in shared memory first (coalesced), then E/4 lanes share a row (one float4 each):
+// a warp-wide LDG.128 covers 32/(E/4) whole rows -- full sectors and 8x fewer L1 wavefronts than one-row-per-lane
+// gathers -- with 8 rows (24 LDG.128) in flight per thread.  The transposed shared-memory store is conflict-free
+// because RP = R + 1.  Callers must barrier before reading X / IDX (stage_load does).
 template <int E, typename SM>
-__device__ __forceinline__ void edge_hidden(const SM& sm, const int (&slot)[RowCfg<E>::TM], const bool (&valid)[RowCfg<E>::TM],
-                                            const int32_t* __restrict__ csr_src, const int32_t* __restrict__ csr_dst,
-                                            const float* __restrict__ A, const float* __restrict__ B,
-                                            const float* __restrict__ PQ) {
+__device__ __forceinline__ void edge_hidden(const SM& sm, int slot0, int n_slots, const int32_t* __restrict__ csr_src,
+                                            const int32_t* __restrict__ csr_dst, const float* __restrict__ A,
+                                            const float* __restrict__ B, const float* __restrict__ PQ) {
   using Cf = RowCfg<E>;
-  constexpr int TM = Cf::TM, RP = Cf::RP;
-#pragma unroll
-  for (int r = 0; r < TM; ++r) {
-    float* col = sm.X + threadIdx.x + r * kRtThreads;
-    int d = -1;
-    if (valid[r]) {
-      const int s = csr_src[slot[r]];
-      d = csr_dst[slot[r]];
-      const float4* a4 = reinterpret_cast<const float4*>(A + (size_t)s * E);
-      const float4* b4 = reinterpret_cast<const float4*>(B + (size_t)d * E);
-      const float4* p4 = reinterpret_cast<const float4*>(PQ + (size_t)slot[r] * E);
-#pragma unroll
-      for (int n = 0; n < E / 4; ++n) {
-        const float4 a = __ldg(a4 + n), b = __ldg(b4 + n), p = __ldg(p4 + n);
-        col[(4 * n) * RP] = fmaxf(a.x + b.x + p.x, 0.0f);
-        col[(4 * n + 1) * RP] = fmaxf(a.y + b.y + p.y, 0.0f);
-        col[(4 * n + 2) * RP] = fmaxf(a.z + b.z + p.z, 0.0f);
-        col[(4 * n + 3) * RP] = fmaxf(a.w + b.w + p.w, 0.0f);
-      }
-    } else {
-#pragma unroll
-      for (int n = 0; n < E; ++n) col[n * RP] = 0.0f;
+  constexpr int R = Cf::R, RP = Cf::RP;
+  constexpr int LPR = E / 4;                 // lanes per row
+  constexpr int RPP = kRtThreads / LPR;      // rows per pass of the CTA
+  for (int i = threadIdx.x; i < R; i += kRtThreads) {
+    const int slot = slot0 + i;
+    const bool ok = slot < n_slots;
+    sm.SRC[i] = ok ? __ldg(csr_src + slot) : -1;
+    sm.IDX[i] = ok ? __ldg(csr_dst + slot) : -1;
+  }
+  __syncthreads();
+  const int q = threadIdx.x % LPR;
+  const int rsub = threadIdx.x / LPR;
+#pragma unroll 8
+  for (int r = rsub; r < R; r += RPP) {
+    const int s = sm.SRC[r], d = sm.IDX[r];
+    float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (s >= 0) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(A + (size_t)s * E) + q);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(B + (size_t)d * E) + q);
+      const float4 p = __ldg(reinterpret_cast<const float4*>(PQ + (size_t)(slot0 + r) * E) + q);
+      h.x = fmaxf(a.x + b.x + p.x, 0.0f);
+      h.y = fmaxf(a.y + b.y + p.y, 0.0f);
+      h.z = fmaxf(a.z + b.z + p.z, 0.0f);
+      h.w = fmaxf(a.w + b.w + p.w, 0.0f);
     }
-    sm.IDX[threadIdx.x + r * kRtThreads] = d;
+    float* x = sm.X + (4 * q) * RP + r;
+    x[0] = h.x; x[RP] = h.y; x[2 * RP] = h.z; x[3 * RP] = h.w;
   }
 }
 
@@ -722,14 +729,7 @@ __global__ void __launch_bounds__(kRtThreads, 4) edge_msg_kernel(ExplorerW w, co
   constexpr int TM = Cf::TM, R = Cf::R, RP = Cf::RP;
   extern __shared__ __align__(16) float smem_raw[];
   Smem<E, false> sm(smem_raw);
-  int slot[TM];
-  bool valid[TM];
-#pragma unroll
-  for (int r = 0; r < TM; ++r) {
-    slot[r] = blockIdx.x * R + r * kRtThreads + threadIdx.x;
-    valid[r] = slot[r] < n_slots;
-  }
-  edge_hidden<E>(sm, slot, valid, csr_src, csr_dst, A, B, P);
+  edge_hidden<E>(sm, blockIdx.x * R, n_slots, csr_src, csr_dst, A, B, P);
   float acc[TM][E];
   stage_load(sm.WB, W + w.l0_2, E * E + E);
   acc_zero(acc);
@@ -781,7 +781,7 @@ __global__ void __launch_bounds__(kRtThreads, 4) policy_kernel(ExplorerW w, cons
     slot[r] = blockIdx.x * R + r * kRtThreads + threadIdx.x;
     valid[r] = slot[r] < n_slots;
   }
-  edge_hidden<E>(sm, slot, valid, csr_src, csr_dst, G, Hp, Q);
+  edge_hidden<E>(sm, blockIdx.x * R, n_slots, csr_src, csr_dst, G, Hp, Q);
   float acc[TM][E];
   stage_load(sm.WB, W + w.p2, E * E + 2 * E);
   acc_zero(acc);

@@ -86,7 +86,7 @@ __device__ __forceinline__ void map_block(const SM& sm, const float* __restrict_
   float acc[TM][E];
   float m[TM], l[TM];
 
-  // self score  s = x^T (scale Wq^T Wk) x                                   (model.py:175, /temperature :177)
+  // self score  s = x^T (scale Wq^T Wk) x, scale = log2(e)/temperature      (model.py:175,177)
   stage_load(sm.WB, W + bw.Gt, E * E);
   acc_zero(acc);
   gemm_smem<E, E, TM, RP>(acc, xcol, sm.WB);
@@ -117,13 +117,13 @@ __device__ __forceinline__ void map_block(const SM& sm, const float* __restrict_
 #pragma unroll
       for (int o = 0; o < OT; ++o) tmax = (o < o_left) ? fmaxf(tmax, s[r][o]) : tmax;
       const float mnew = fmaxf(m[r], tmax);
-      const float corr = expf(m[r] - mnew);
+      const float corr = exp2f(m[r] - mnew);
       float lsum = l[r] * corr;
 #pragma unroll
       for (int n = 0; n < E; ++n) acc[r][n] *= corr;
 #pragma unroll
       for (int o = 0; o < OT; ++o) {
-        const float p = (o < o_left) ? expf(s[r][o] - mnew) : 0.0f;
+        const float p = (o < o_left) ? exp2f(s[r][o] - mnew) : 0.0f;
         lsum += p;
         s[r][o] = p;
       }
@@ -536,33 +536,22 @@ __global__ void __launch_bounds__(kRtThreads, 3) edge_feature_kernel(
   for (int r = 0; r < TM; ++r)
     if (valid[r]) acc_store_global<TM, E>(acc, r, Q + (size_t)slot[r] * E);
   // P = W4 ef + W5 ec + b  : loop-invariant part of lin_0[0]                (model.py:39,142)
-  // W4 ef is parked in X (ef is dead after this), edge_code is chained through registers.
+  // W4 ef stays in registers while edge_code is produced in place in X (ef is dead after this GEMM).
+  float pacc[TM][E];
   stage_load(sm.WB, W + w.l0_ef, E * E);
-  acc_zero(acc);
-  gemm_smem<E, E, TM, RP>(acc, xcol, sm.WB);
-  acc_store<TM, E, RP>(acc, xcol);
+  acc_zero(pacc);
+  gemm_smem<E, E, TM, RP>(pacc, xcol, sm.WB);
   {
     float in[TM][2 * C];
     gather_in(in);
-    stage_load(sm.WB, W + w.ec0, 2 * C * E + E);                             // edge_code, model.py:120
-    acc_zero(acc);
-    gemm_reg<2 * C, E, TM>(acc, in, sm.WB);
-    acc_add_vec(acc, sm.WB + 2 * C * E);
-    acc_relu(acc);
+    encoder_mlp<2 * C, E>(sm, W, w.ec0, w.ec2, in, xcol, xcol);              // edge_code, model.py:120
   }
-  float ec[TM][E];
-  stage_load(sm.WB, W + w.ec2, E * E + E);
-  acc_zero(ec);
-  gemm_reg<E, E, TM>(ec, acc, sm.WB);
-  acc_add_vec(ec, sm.WB + E * E);
   stage_load(sm.WB, W + w.l0_ec, E * E + E);
-  acc_zero(acc);
-  gemm_reg<E, E, TM>(acc, ec, sm.WB);
-  acc_add_vec(acc, sm.WB + E * E);
-  acc_add_col<TM, E, RP>(acc, xcol);
+  gemm_smem<E, E, TM, RP>(pacc, xcol, sm.WB);
+  acc_add_vec(pacc, sm.WB + E * E);
 #pragma unroll
   for (int r = 0; r < TM; ++r)
-    if (valid[r]) acc_store_global<TM, E>(acc, r, P + (size_t)slot[r] * E);
+    if (valid[r]) acc_store_global<TM, E>(pacc, r, P + (size_t)slot[r] * E);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -879,7 +868,9 @@ int explorer_build_image(ExplorerModel& m) {
   // ---- pack
   Packer pk;
   ExplorerW& w = m.w;
-  const double scale = 1.0 / std::sqrt((double)e);  // 1 / temperature (model.py:208)
+  // 1 / temperature (model.py:208) times log2(e): scores are produced in base-2 units so that the softmax weights are
+  // exp2(s - max) -- one MUFU.EX2 instead of the expf sequence; mathematically the same softmax
+  const double scale = 1.4426950408889634074 / std::sqrt((double)e);
   auto lin_pack = [&](const std::string& name, int in) {  // [Wt | b]
     int off = pk.begin();
     pk.put(transpose_window(T(name + ".weight"), e, in, 0, in));

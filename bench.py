@@ -183,7 +183,7 @@ def run_reference(args, wl, rank, world):
         "note": "reference PyG path not installable (torch_geometric/torch_cluster/torch_sparse absent, no network): "
                 "timed the oracle restatement of eval_gnn.create_data + model.py forward + maze_env._edge_fp on the host cores",
     }
-    print(json.dumps(line))
+    _emit(line)
 
 
 def workload_config(args, wl, world):
@@ -195,6 +195,16 @@ def workload_config(args, wl, world):
 
 
 # --------------------------------------------------------------------------------------------------------------
+def _emit(line):
+    """Write the ONE JSON line to the real stdout (fd saved before library chatter was redirected to stderr)."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+# Libraries (NCCL "version" banner, torch warnings) print to fd 1; keep stdout for the JSON line only.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -408,7 +418,7 @@ def main():
         gps, dt, _ = cpu_graphs_per_sec(wl, list(range(args.cpu_sample)), threads)
         line["cpu_baseline"] = {"value": gps, "unit": "graphs/s", "cores": threads, "kind": "port",
                                 "sample": "first %d graphs of the workload (oracle: knn graph + explorer forward + edge checks), %.1f s" % (args.cpu_sample, dt)}
-    print(json.dumps(line))
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -119,6 +119,82 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) knn_select_kernel(
   }
 }
 
+// Register-strip variant for graphs with at most 32*NPL nodes (the BASELINE sizes: 1000 -> NPL 32, 2000 -> NPL 64):
+// each lane keeps the bit patterns of its NPL candidate distances in registers, so the 31 bisection passes are pure
+// ALU work (no shared-memory re-reads -- the strip version is bound by the single LSU port).  Same selection rule.
+template <int NPL>
+__global__ void __launch_bounds__(kWarpsPerCta * 32) knn_select_reg_kernel(
+    const float* __restrict__ v, int c, const int32_t* __restrict__ node_ptr, const int32_t* __restrict__ n_free,
+    const int32_t* __restrict__ k1s, const int64_t* __restrict__ bm_ptr, int n_graphs, int n_rows_total,
+    uint32_t* __restrict__ bitmap) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pass = blockIdx.y;
+  for (int r = blockIdx.x * kWarpsPerCta + warp; r < n_rows_total; r += gridDim.x * kWarpsPerCta) {
+    const int g = find_graph(node_ptr, n_graphs, r);
+    const int n0 = node_ptr[g], n = node_ptr[g + 1] - n0;
+    const int i = r - n0;
+    const int nf = n_free[g];
+    int cnt;
+    if (pass == 0) cnt = n;
+    else {
+      if (nf >= n || i >= nf) continue;
+      cnt = nf;
+    }
+    const int k = min(k1s[g], cnt);
+    const float* vg = v + (size_t)n0 * c;
+    const int wpr = (n + 31) >> 5;
+    uint32_t* bm = bitmap + bm_ptr[g];
+
+    uint32_t d[NPL];
+#pragma unroll
+    for (int t = 0; t < NPL; ++t) d[t] = 0xffffffffu;   // padding: never below any threshold
+    for (int q = 0; q < c; ++q) {
+      const float xi = __ldg(vg + (size_t)i * c + q);
+#pragma unroll
+      for (int t = 0; t < NPL; ++t) {
+        const int j = lane + 32 * t;
+        if (j < cnt) {
+          const float diff = __fsub_rn(xi, __ldg(vg + (size_t)j * c + q));
+          const float prev = q == 0 ? 0.0f : __uint_as_float(d[t]);
+          d[t] = __float_as_uint(__fadd_rn(prev, __fmul_rn(diff, diff)));
+        }
+      }
+    }
+    uint32_t T = 0xffffffffu;
+    int n_less = cnt;
+    if (k < cnt) {
+      T = 0;
+      for (int bit = 30; bit >= 0; --bit) {
+        const uint32_t cand = T | (1u << bit);
+        int cl = 0;
+#pragma unroll
+        for (int t = 0; t < NPL; ++t) cl += (d[t] < cand) ? 1 : 0;
+        cl = __reduce_add_sync(0xffffffffu, cl);
+        if (cl < k) T = cand;
+      }
+      int cl = 0;
+#pragma unroll
+      for (int t = 0; t < NPL; ++t) cl += (d[t] < T) ? 1 : 0;
+      n_less = __reduce_add_sync(0xffffffffu, cl);
+    }
+    int quota = k - min(n_less, k);
+#pragma unroll
+    for (int t = 0; t < NPL; ++t) {
+      const int j = lane + 32 * t;
+      const bool in = j < cnt;
+      const bool less = in && d[t] < T;
+      const bool tie = in && (d[t] == T) && (k < cnt);
+      const uint32_t tb = __ballot_sync(0xffffffffu, tie);
+      const bool take = less || (tie && __popc(tb & ((1u << lane) - 1u)) < quota);
+      quota -= min(quota, __popc(tb));
+      if (take) {
+        atomicOr(bm + (size_t)i * wpr + (j >> 5), 1u << (j & 31));
+        atomicOr(bm + (size_t)j * wpr + (i >> 5), 1u << (i & 31));
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) row_count_kernel(const uint32_t* __restrict__ bitmap, const int32_t* __restrict__ node_ptr,
                                                         const int64_t* __restrict__ bm_ptr, int n_graphs, int n_rows_total,
                                                         int32_t* __restrict__ row_count) {
@@ -322,8 +398,21 @@ extern "C" int gmp_knn_graph(gmp_handle* /*h*/, int64_t n_graphs, const float* v
     GMP_CUDA(cudaFuncSetAttribute(knn_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int gx = (int)((n_total + kWarpsPerCta - 1) / kWarpsPerCta);
     if (gx > kNumSMs * 16) gx = kNumSMs * 16;
-    knn_select_kernel<<<dim3(gx, 2), kWarpsPerCta * 32, smem, st>>>(v, c, ws.node_ptr, ws.n_free, ws.k1, ws.bm_ptr,
-                                                                    (int)n_graphs, (int)n_total, strip, ws.bitmap);
+    if (max_n <= 256)
+      knn_select_reg_kernel<8><<<dim3(gx, 2), kWarpsPerCta * 32, 0, st>>>(v, c, ws.node_ptr, ws.n_free, ws.k1, ws.bm_ptr, (int)n_graphs,
+                                                                          (int)n_total, ws.bitmap);
+    else if (max_n <= 512)
+      knn_select_reg_kernel<16><<<dim3(gx, 2), kWarpsPerCta * 32, 0, st>>>(v, c, ws.node_ptr, ws.n_free, ws.k1, ws.bm_ptr, (int)n_graphs,
+                                                                           (int)n_total, ws.bitmap);
+    else if (max_n <= 1024)
+      knn_select_reg_kernel<32><<<dim3(gx, 2), kWarpsPerCta * 32, 0, st>>>(v, c, ws.node_ptr, ws.n_free, ws.k1, ws.bm_ptr, (int)n_graphs,
+                                                                           (int)n_total, ws.bitmap);
+    else if (max_n <= 2048)
+      knn_select_reg_kernel<64><<<dim3(gx, 2), kWarpsPerCta * 32, 0, st>>>(v, c, ws.node_ptr, ws.n_free, ws.k1, ws.bm_ptr, (int)n_graphs,
+                                                                           (int)n_total, ws.bitmap);
+    else
+      knn_select_kernel<<<dim3(gx, 2), kWarpsPerCta * 32, smem, st>>>(v, c, ws.node_ptr, ws.n_free, ws.k1, ws.bm_ptr,
+                                                                      (int)n_graphs, (int)n_total, strip, ws.bitmap);
     GMP_LAUNCH_CHECK();
     int gr = (int)((n_total + 7) / 8);
     if (gr > kNumSMs * 16) gr = kNumSMs * 16;

@@ -67,6 +67,42 @@ def to_np(tensor):
     return tensor.data.cpu().numpy()
 
 
+def eval_gnn(str, seed, env, indexes, model=None, model_s=None, use_tqdm=False, smooth=True, batch=500, t_max=500, k=30,
+             weights_root=".", **kwargs):
+    """eval_gnn.py:96-145: run `explore` over a list of problems and reduce the per-problem tuples."""
+    import random
+    from .str2name import str2name
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    random.seed(seed)                                           # config.set_random_seed (config.py:48-51)
+    import os
+    if model is None:
+        _, model, model_path, _, _ = str2name(str, make_env=False)
+        model.load_state_dict(torch.load(os.path.join(weights_root, model_path), map_location="cpu"))
+    if model_s is None and smooth:
+        _, _, _, model_s, model_s_path = str2name(str, make_env=False)
+        model_s.load_state_dict(torch.load(os.path.join(weights_root, model_s_path), map_location="cpu"))
+    model.eval()
+    if model_s is not None:
+        model_s.eval()
+    solutions, paths, smooth_paths = [], [], []
+    for index in indexes:
+        env.init_new_problem(index)
+        result = explore(env, model, model_s, smooth, batch=batch, t_max=t_max, k=k, **kwargs)
+        paths.append(result['path'])
+        smooth_paths.append(result['smooth_path'])
+        solutions.append((result['success'], path_cost(result['path']), path_cost(result['smooth_path']), result['c_explore'],
+                          result['c_smooth'], result['total'], result['total_explore']))
+    n_success = sum([s[0] for s in solutions])
+    collision_explore = np.mean([s[3] for s in solutions])
+    collision = np.mean([(s[3] + s[4]) for s in solutions])
+    running_time = float(sum([s[5] for s in solutions if s[0]])) / max(n_success, 1)
+    solution_cost = float(sum([(s[2]) for s in solutions if s[0]])) / max(n_success, 1)
+    total_time = sum([s[5] for s in solutions])
+    total_time_explore = sum([s[6] for s in solutions])
+    return n_success, collision, running_time, solution_cost, total_time, paths, smooth_paths, collision_explore, total_time_explore
+
+
 def create_data(free, collided, env, k):
     """eval_gnn.py:150-165.  Returns ``Data(goal, v, labels, edge_index)``; tensors live on the GPU."""
     device = _device()

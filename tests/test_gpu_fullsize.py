@@ -1,0 +1,103 @@
+"""GPU: BASELINE-size checks through size-independent properties: at N=1000, k=50 the oracle is too
+slow to run per graph for a whole batch, so the batched CUDA path is checked by (i) batch invariance -- a graph scores
+bit-identically alone and inside a 24-graph packed batch, (ii) dense == sparse scatter, (iii) node-permutation
+equivariance, (iv) one full-size graph against the oracle at the 1e-4 gate, (v) collision symmetry + check-count
+bounds over every edge of the batch, (vi) the planner-facing factory."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _batch(dev, B=24, n=1000, k=50, c=2):
+    from gnn_motion_planning_b200 import graph
+    maps = np.load(os.path.join(G, "maze_maps_256.npz"))["maps"]
+    vs, obss = [], []
+    for g in range(B):
+        rng = np.random.default_rng(1234 + g)
+        vs.append(rng.uniform(-1, 1, (n, c)).astype(np.float32))
+        obss.append((np.argwhere(maps[g] == 1) / 15.0 - 0.5).astype(np.float32))
+    v = torch.from_numpy(np.concatenate(vs)).to(dev)
+    node_ptr = (np.arange(B + 1) * n).astype(np.int32)
+    ei, edge_ptr = graph.knn_graph_batch(v, node_ptr, np.full(B, n), np.full(B, k))
+    obs = torch.from_numpy(np.concatenate(obss)).to(dev)
+    obs_ptr = np.cumsum([0] + [len(o) for o in obss]).astype(np.int32)
+    goal = torch.from_numpy(np.stack([x[1] for x in vs])).to(dev)
+    return vs, obss, v, ei, edge_ptr, node_ptr, obs, obs_ptr, goal, maps
+
+
+def test_c2_batch_properties(cuda_device):
+    from gnn_motion_planning_b200 import collision
+    from gnn_motion_planning_b200.model import EncoderProcessDecoder
+    from oracle import explorer as o_explorer
+    dev = cuda_device
+    sd = torch.load(os.path.join(G, "weights", "weights_maze.pt"), map_location="cpu")
+    m = EncoderProcessDecoder(2, 2, 32, 2).to(dev)
+    m.load_state_dict(sd)
+    vs, obss, v, ei, edge_ptr, node_ptr, obs, obs_ptr, goal, maps = _batch(dev)
+    et = int(edge_ptr[-1])
+    logits = m.forward_batch(v, ei, goal, obs, node_ptr, edge_ptr, obs_ptr, loop=5).clone()
+    assert torch.isfinite(logits[:et]).all()
+    # (i) batch invariance + (ii) dense == sparse, on three graphs of the batch
+    for g in (0, 7, 23):
+        e0, e1 = int(edge_ptr[g]), int(edge_ptr[g + 1])
+        eg = ei[:, e0:e1].contiguous()
+        vg = v[node_ptr[g]:node_ptr[g + 1]]
+        og = obs[obs_ptr[g]:obs_ptr[g + 1]]
+        alone = m.forward_sparse(goal=goal[g], loop=5, v=vg, obstacles=og, edge_index=eg)
+        assert torch.equal(alone, logits[e0:e1]), g
+        dense = m(goal=goal[g], loop=5, v=vg, obstacles=og, edge_index=eg)
+        assert torch.equal(dense[eg[1], eg[0]], alone)
+        assert int((dense != 0).sum()) <= e1 - e0
+    # (iii) node-permutation equivariance on one full-size graph
+    g = 3
+    e0, e1 = int(edge_ptr[g]), int(edge_ptr[g + 1])
+    eg = ei[:, e0:e1]
+    n = 1000
+    perm = torch.randperm(n, generator=torch.Generator().manual_seed(1)).to(dev)
+    inv = torch.empty_like(perm)
+    inv[perm] = torch.arange(n, device=dev)
+    vg = v[node_ptr[g]:node_ptr[g + 1]]
+    og = obs[obs_ptr[g]:obs_ptr[g + 1]]
+    a = m.forward_sparse(goal=goal[g], loop=5, v=vg, obstacles=og, edge_index=eg.contiguous())
+    b = m.forward_sparse(goal=goal[g], loop=5, v=vg[perm].contiguous(), obstacles=og, edge_index=inv[eg].contiguous())
+    assert float((a - b).abs().max()) < 1e-4
+    # (iv) one full-size graph against the oracle
+    want = o_explorer.explorer_forward(sd, torch.from_numpy(vs[g]), eg.cpu(), torch.from_numpy(vs[g][1]), torch.from_numpy(obss[g]),
+                                       loop=5, dense=False)
+    assert float((a.cpu() - want).abs().max()) < 1e-4
+    # (v) collision over every edge of the batch: symmetric, counts within [0 | 1 | 2 .. 2+127]
+    maps_d = torch.from_numpy(maps).to(dev)
+    node_ptr_d, edge_ptr_d = torch.from_numpy(node_ptr).to(dev), torch.from_numpy(edge_ptr).to(dev)
+    free, checks = collision.maze_edge_fp_graph(v, ei, node_ptr_d, edge_ptr_d, maps_d, et, want_checks=True)
+    flipped = torch.stack([ei[1, :et], ei[0, :et]]).contiguous()
+    free_r, _ = collision.maze_edge_fp_graph(v, flipped, node_ptr_d, edge_ptr_d, maps_d, et, want_checks=True)
+    assert torch.equal(free, free_r)                                   # _edge_fp(a,b) == _edge_fp(b,a) in the 2-D maze
+    assert int(checks.min()) >= 1 and int(checks.max()) <= 129
+    self_loops = ei[0, :et] == ei[1, :et]
+    gid = torch.repeat_interleave(torch.arange(len(edge_ptr) - 1, device=dev), torch.from_numpy(np.diff(edge_ptr)).to(dev))
+    pts = v[(ei[0, :et] + node_ptr_d[gid])[self_loops]]
+    st = collision.maze_state_fp(pts, maps_d, gid[self_loops].to(torch.int32))
+    assert torch.equal(st, free[self_loops])                            # a self loop is free iff its endpoint is
+    rows = collision.result_rows(logits, free, edge_ptr_d, 100)
+    assert torch.equal(rows[:, 0].cpu(), torch.arange(100, 124, dtype=torch.float32))
+    assert torch.equal(rows[:, 1].cpu(), torch.from_numpy(np.diff(edge_ptr).astype(np.float32)))
+    for g in (0, 11):
+        e0, e1 = int(edge_ptr[g]), int(edge_ptr[g + 1])
+        assert float(rows[g, 2]) == float(free[e0:e1].sum()) and float(rows[g, 3]) == float(logits[e0:e1].max())
+
+
+def test_str2name_factory(cuda_device):
+    from gnn_motion_planning_b200.str2name import TABLE, str2name
+    for name, (ws, c, e, s, *_rest) in TABLE.items():
+        env, model, mp, model_s, sp = str2name(name, make_env=False)
+        assert env is None and model.config_size == c and model.embed_size == e and model.obs_size == s
+        assert model_s.config_size == c and model_s.embed_size == 128
+        assert mp.startswith("data/weights/") and sp.startswith("data/weights/")
+    assert str2name("ur5", make_env=False)[3].scale == pytest.approx(2 * np.pi)
+    with pytest.raises(KeyError):
+        str2name("maze3", make_env=False)

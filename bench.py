@@ -385,7 +385,10 @@ def main():
     sm_mhz = (clocks or {}).get("sm_mhz") or 1900.0
     fp32_peak_tf = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
     msg_ms = phase_ms["edge_msg"] / K / 5.0
-    msg_bytes = et * wl["e"] * 4 + et * (2 * wl["e"] * 4 + 8)   # P stream + gathered A[src], B[dst] rows + csr ids (L2-resident gathers)
+    # algorithmic HBM bytes of one message round: the loop-invariant edge term P (e*4 B/edge, streamed by TMA bulk copies)
+    # + the CSR (src, dst) ids (8 B/edge).  The gathered A[src] / B[dst] rows (2*e*4 B/edge) are L2-resident (2 x 33 MB
+    # per 256-graph batch) and are NOT counted.
+    msg_bytes = et * (wl["e"] * 4 + 8)
     line = {
         "metric": "explorer_graphs_per_sec", "value": graphs_per_s, "unit": "graphs/s", "n_gpus": world, "steps": K,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -687,63 +687,160 @@ __device__ __forceinline__ void edge_hidden(const SM& sm, int slot0, int n_slots
   __syncthreads();
   const int q = threadIdx.x % LPR;
   const int rsub = threadIdx.x / LPR;
-#pragma unroll 8
-  for (int r = rsub; r < R; r += RPP) {
-    const int s = sm.SRC[r], d = sm.IDX[r];
-    float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (s >= 0) {
-      const float4 a = __ldg(reinterpret_cast<const float4*>(A + (size_t)s * E) + q);
-      const float4 b = __ldg(reinterpret_cast<const float4*>(B + (size_t)d * E) + q);
-      const float4 p = __ldg(reinterpret_cast<const float4*>(PQ + (size_t)(slot0 + r) * E) + q);
-      h.x = fmaxf(a.x + b.x + p.x, 0.0f);
-      h.y = fmaxf(a.y + b.y + p.y, 0.0f);
-      h.z = fmaxf(a.z + b.z + p.z, 0.0f);
-      h.w = fmaxf(a.w + b.w + p.w, 0.0f);
+  constexpr int UB = 8;   // rows per thread in flight: all 24 row loads are issued before the first is consumed
+  for (int base = rsub; base < R; base += UB * RPP) {
+    float4 av[UB], bv[UB], pv[UB];
+    int sv[UB];
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
+      const int r = base + u * RPP;
+      const int s = sm.SRC[r], d = sm.IDX[r];
+      sv[u] = s;
+      av[u] = __ldg(reinterpret_cast<const float4*>(A + (size_t)max(s, 0) * E) + q);
+      bv[u] = __ldg(reinterpret_cast<const float4*>(B + (size_t)max(d, 0) * E) + q);
+      pv[u] = s >= 0 ? __ldg(reinterpret_cast<const float4*>(PQ + (size_t)(slot0 + r) * E) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    float* x = sm.X + (4 * q) * RP + r;
-    x[0] = h.x; x[RP] = h.y; x[2 * RP] = h.z; x[3 * RP] = h.w;
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
+      const int r = base + u * RPP;
+      const bool ok = sv[u] >= 0;
+      float* x = sm.X + (4 * q) * RP + r;
+      x[0] = ok ? fmaxf(av[u].x + bv[u].x + pv[u].x, 0.0f) : 0.0f;
+      x[RP] = ok ? fmaxf(av[u].y + bv[u].y + pv[u].y, 0.0f) : 0.0f;
+      x[2 * RP] = ok ? fmaxf(av[u].z + bv[u].z + pv[u].z, 0.0f) : 0.0f;
+      x[3 * RP] = ok ? fmaxf(av[u].w + bv[u].w + pv[u].w, 0.0f) : 0.0f;
+    }
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 // messages + max aggregation for one round; rows = CSR slots, flat over the batch   (model.py:33,38-41)
 // ------------------------------------------------------------------------------------------------
+// Persistent CTAs (grid = resident CTAs, tiles strided over them).  Per tile:
+//   wait for the tile's P block in the staging buffer (landed there by a TMA bulk copy issued one tile earlier);
+//   hidden = relu(A[src] + B[dst] + P) -> X          (P from shared memory, A / B rows gathered from L2, coalesced);
+//   issue the TMA bulk copy of the NEXT tile's P block into the staging buffer  -- the HBM stream of the
+//   loop-invariant edge term is therefore always one tile ahead of the FMAs;
+//   m = lin_0[2](hidden)  (weights staged once per CTA);  segmented max -> RED.MAX.
 template <int E>
-__global__ void __launch_bounds__(kRtThreads, 4) edge_msg_kernel(ExplorerW w, const float* __restrict__ W, int n_slots,
+struct MsgSmem {
+  using Cf = RowCfg<E>;
+  static constexpr int kX = E * Cf::RP;
+  static constexpr int kPS = Cf::R * E;          // staging buffer for one P tile, row-major like global memory
+  static constexpr int kWB = E * E + 2 * E;
+  static constexpr size_t kBytes = (size_t)(kX + kPS + kWB) * sizeof(float) + 2 * Cf::R * sizeof(int) + 16;
+};
+
+template <int E>
+__global__ void __launch_bounds__(kRtThreads, 3) edge_msg_kernel(ExplorerW w, const float* __restrict__ W, int n_slots,
                                                                  const int32_t* __restrict__ csr_src,
                                                                  const int32_t* __restrict__ csr_dst, const float* __restrict__ A,
                                                                  const float* __restrict__ B, const float* __restrict__ P,
                                                                  float* __restrict__ AGG) {
   using Cf = RowCfg<E>;
+  using MS = MsgSmem<E>;
   constexpr int TM = Cf::TM, R = Cf::R, RP = Cf::RP;
-  extern __shared__ __align__(16) float smem_raw[];
-  Smem<E, false> sm(smem_raw);
-  edge_hidden<E>(sm, blockIdx.x * R, n_slots, csr_src, csr_dst, A, B, P);
-  float acc[TM][E];
-  stage_load(sm.WB, W + w.l0_2, E * E + E);
-  acc_zero(acc);
-  gemm_smem<E, E, TM, RP>(acc, sm.X + threadIdx.x, sm.WB);
-  acc_add_vec(acc, sm.WB + E * E);
-  acc_store<TM, E, RP>(acc, sm.X + threadIdx.x);   // in place: a thread only ever read its own columns of X
-  __syncthreads();
-  // segmented max: thread = (feature n, row group); rows of a group are walked in CSR order, so a
-  // target's rows are consecutive; one RED per (segment, feature), 128 B coalesced across the warp.
-  constexpr int GROUPS = kRtThreads / E;
-  constexpr int ROWS = R / GROUPS;
-  const int n = threadIdx.x % E;
-  const int r0 = (threadIdx.x / E) * ROWS;
-  int cur = sm.IDX[r0];
-  float run = -INFINITY;
-  for (int i = 0; i < ROWS; ++i) {
-    const int d = sm.IDX[r0 + i];
-    if (d != cur) {
-      if (cur >= 0) atomic_max_f32(AGG + (size_t)cur * E + n, run);
-      cur = d;
-      run = -INFINITY;
-    }
-    run = fmaxf(run, sm.X[n * RP + r0 + i]);
+  constexpr int LPR = E / 4, RPP = kRtThreads / LPR;
+  extern __shared__ __align__(128) float smem_raw[];
+  float* PS = smem_raw;                       // first: 128 B aligned for the bulk copy
+  float* X = PS + MS::kPS;
+  float* WB = X + MS::kX;
+  int* IDX = reinterpret_cast<int*>(WB + MS::kWB);
+  int* SRC = IDX + R;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(SRC + R);
+  const int n_tiles = (n_slots + R - 1) / R;
+  int tile = blockIdx.x;
+  if (tile >= n_tiles) return;
+  auto tile_bytes = [&](int t) { return (uint32_t)(min(R, n_slots - t * R) * E * (int)sizeof(float)); };
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    mbar_expect_tx(bar, tile_bytes(tile));
+    tma_bulk_g2s(PS, P + (size_t)tile * R * E, tile_bytes(tile), bar);
   }
-  if (cur >= 0) atomic_max_f32(AGG + (size_t)cur * E + n, run);
+  // weights of lin_0[2], once per CTA
+  for (int i = threadIdx.x; i < (E * E + E) / 4; i += kRtThreads)
+    reinterpret_cast<float4*>(WB)[i] = __ldg(reinterpret_cast<const float4*>(W + w.l0_2) + i);
+  uint32_t phase = 0;
+  const int q = threadIdx.x % LPR, rsub = threadIdx.x / LPR;
+  constexpr int IPT = R / kRtThreads;          // CSR indices per thread and tile
+  int nsrc[IPT], ndst[IPT];
+  auto load_indices = [&](int t) {
+#pragma unroll
+    for (int u = 0; u < IPT; ++u) {
+      const int slot = t * R + u * kRtThreads + threadIdx.x;
+      const bool ok = t < n_tiles && slot < n_slots;
+      nsrc[u] = ok ? __ldg(csr_src + slot) : -1;
+      ndst[u] = ok ? __ldg(csr_dst + slot) : -1;
+    }
+  };
+  load_indices(tile);
+  for (; tile < n_tiles; tile += gridDim.x) {
+#pragma unroll
+    for (int u = 0; u < IPT; ++u) {
+      SRC[u * kRtThreads + threadIdx.x] = nsrc[u];
+      IDX[u * kRtThreads + threadIdx.x] = ndst[u];
+    }
+    __syncthreads();           // indices visible; mbarrier init visible (first tile); X free (previous scan done)
+    load_indices(tile + gridDim.x);   // next tile's indices travel while this tile is processed
+    mbar_wait(bar, phase);     // this tile's P block has landed
+    phase ^= 1;
+    // 8 rows per thread in flight: all 16 row gathers are issued before the first is consumed
+    constexpr int UB = 8;
+    for (int base = rsub; base < R; base += UB * RPP) {
+      float4 av[UB], bv[UB];
+      int sv[UB];
+#pragma unroll
+      for (int u = 0; u < UB; ++u) {
+        const int r = base + u * RPP;
+        const int s = SRC[r], d = IDX[r];
+        sv[u] = s;
+        av[u] = __ldg(reinterpret_cast<const float4*>(A + (size_t)max(s, 0) * E) + q);
+        bv[u] = __ldg(reinterpret_cast<const float4*>(B + (size_t)max(d, 0) * E) + q);
+      }
+#pragma unroll
+      for (int u = 0; u < UB; ++u) {
+        const int r = base + u * RPP;
+        const float4 p = *reinterpret_cast<const float4*>(PS + r * E + 4 * q);
+        const bool ok = sv[u] >= 0;
+        float* x = X + (4 * q) * RP + r;
+        x[0] = ok ? fmaxf(av[u].x + bv[u].x + p.x, 0.0f) : 0.0f;
+        x[RP] = ok ? fmaxf(av[u].y + bv[u].y + p.y, 0.0f) : 0.0f;
+        x[2 * RP] = ok ? fmaxf(av[u].z + bv[u].z + p.z, 0.0f) : 0.0f;
+        x[3 * RP] = ok ? fmaxf(av[u].w + bv[u].w + p.w, 0.0f) : 0.0f;
+      }
+    }
+    __syncthreads();           // X complete; staging buffer consumed
+    const int next = tile + gridDim.x;
+    if (threadIdx.x == 0 && next < n_tiles) {
+      mbar_expect_tx(bar, tile_bytes(next));
+      tma_bulk_g2s(PS, P + (size_t)next * R * E, tile_bytes(next), bar);
+    }
+    float acc[TM][E];
+    acc_zero(acc);
+    gemm_smem<E, E, TM, RP>(acc, X + threadIdx.x, WB);
+    acc_add_vec(acc, WB + E * E);
+    acc_store<TM, E, RP>(acc, X + threadIdx.x);   // in place: a thread only ever read its own columns of X
+    __syncthreads();
+    // segmented max: thread = (feature n, row group); rows of a group are walked in CSR order, so a
+    // target's rows are consecutive; one RED per (segment, feature), 128 B coalesced across the warp.
+    constexpr int GROUPS = kRtThreads / E;
+    constexpr int ROWS = R / GROUPS;
+    const int n = threadIdx.x % E;
+    const int r0 = (threadIdx.x / E) * ROWS;
+    int cur = IDX[r0];
+    float run = -INFINITY;
+    for (int i = 0; i < ROWS; ++i) {
+      const int d = IDX[r0 + i];
+      if (d != cur) {
+        if (cur >= 0) atomic_max_f32(AGG + (size_t)cur * E + n, run);
+        cur = d;
+        run = -INFINITY;
+      }
+      run = fmaxf(run, X[n * RP + r0 + i]);
+    }
+    if (cur >= 0) atomic_max_f32(AGG + (size_t)cur * E + n, run);
+    __syncthreads();           // IDX / X reused by the next tile
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1073,7 +1170,7 @@ int run_forward(gmp_handle* h, int64_t B, const float* v, const int64_t* edge_in
     GMP_CUDA(cudaFuncSetAttribute(node_pre_kernel<C, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     GMP_CUDA(cudaFuncSetAttribute(edge_feature_kernel<C, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
     GMP_CUDA(cudaFuncSetAttribute(node_loop_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GMP_CUDA(cudaFuncSetAttribute(edge_msg_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+    GMP_CUDA(cudaFuncSetAttribute(edge_msg_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MsgSmem<E>::kBytes));
     GMP_CUDA(cudaFuncSetAttribute(policy_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
     attr_done = true;
   }
@@ -1128,6 +1225,12 @@ int run_forward(gmp_handle* h, int64_t B, const float* v, const int64_t* edge_in
   }
   tl.end(st);
   const int node_tiles = (int)((Nt + R - 1) / R), slot_tiles = (int)((Et + R - 1) / R);
+  static int msg_grid = 0;   // persistent grid of the message kernel: every resident CTA slot of the device
+  if (msg_grid == 0) {
+    int per_sm = 0;
+    GMP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, edge_msg_kernel<E>, kRtThreads, MsgSmem<E>::kBytes));
+    msg_grid = kNumSMs * std::max(per_sm, 1);
+  }
   for (int it = 0; it <= loop; ++it) {
     const int mode = it == loop ? 2 : (it == 0 ? 0 : 1);
     if (node_tiles > 0) {
@@ -1138,7 +1241,8 @@ int run_forward(gmp_handle* h, int64_t B, const float* v, const int64_t* edge_in
     }
     if (it < loop && slot_tiles > 0) {
       tl.begin(kPhEdgeMsg, st);
-      edge_msg_kernel<E><<<slot_tiles, kRtThreads, smem1, st>>>(m.w, W, (int)Et, ws.csr_src, ws.csr_dst, ws.A, ws.B, ws.P, ws.AGG);
+      edge_msg_kernel<E><<<std::min(slot_tiles, msg_grid), kRtThreads, MsgSmem<E>::kBytes, st>>>(m.w, W, (int)Et, ws.csr_src, ws.csr_dst, ws.A, ws.B,
+                                                                                                ws.P, ws.AGG);
       GMP_LAUNCH_CHECK();
       tl.end(st);
     }

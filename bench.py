@@ -265,49 +265,33 @@ def main():
     model.eval()
     model.set_timing(True)
 
-    # ---- device-resident copies for the kernel-only measurement
+    # ---- the public batched API (gnn_motion_planning_b200.batch.HotPath) drives both measurements
+    from gnn_motion_planning_b200.batch import HotPath
     v_d, goal_d, obs_d = v_h.to(dev), goal_h.to(dev), obs_h.to(dev)
     maps_d, prob_d = maps_h.to(dev), prob_h.to(dev)
-    node_ptr_d = torch.from_numpy(node_ptr).to(dev)
-    cap = int(sum(_lib.load().gmp_knn_graph_max_edges(N, int(wl["k"])) for _ in range(B)))
-    ei_buf = torch.empty((2, cap), dtype=torch.int64, device=dev)
-    logits_buf = torch.empty(cap, dtype=torch.float32, device=dev)
-    free_buf = torch.empty(cap, dtype=torch.uint8, device=dev)
-    checks_buf = torch.empty(cap, dtype=torch.int32, device=dev)
-    rows_buf = torch.empty((B, 4), dtype=torch.float32, device=dev)
+    if is_maze:
+        hp = HotPath(model, B, N, wl["k"], kind="maze", maps=maps_d, first_problem_id=rank * B, device=dev)
+    else:
+        hp = HotPath(model, B, N, wl["k"], kind="arm", boxes=boxes_d, box_ptr=box_ptr_d, arm_model=ARM_MODEL[wl["env"]], rrt_eps=0.5,
+                     first_problem_id=rank * B, device=dev)
     gather_buf = torch.empty((world, B, 4), dtype=torch.float32, device=dev) if world > 1 else None
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
     phase_ms = {}
     state = {}
 
-    def step(v, goal, obs, maps, prob, timed=False):
-        e0, e1, e2, e3 = ev(), ev(), ev(), ev()
-        e0.record()
-        ei, edge_ptr = graph.knn_graph_batch(v, node_ptr, n_free, k1, edge_index_out=ei_buf)   # syncs on edge_ptr (B+1 ints)
-        e1.record()
-        et = int(edge_ptr[-1])
-        logits = model.forward_batch(v, ei, goal, obs, node_ptr, edge_ptr, obs_ptr, loop=5, dense=False, out=logits_buf)
-        e2.record()
-        edge_ptr_d = torch.from_numpy(edge_ptr).to(dev, non_blocking=True)
-        if is_maze:
-            collision.maze_edge_fp_graph(v, ei, node_ptr_d, edge_ptr_d, maps, et, problem_of_graph=prob, want_checks=True,
-                                         free_out=free_buf, checks_out=checks_buf)
-        else:
-            collision.arm_edge_fp_graph(ARM_MODEL[wl["env"]], v, ei, node_ptr_d, edge_ptr_d, boxes_d, box_ptr_d, et, rrt_eps=0.5,
-                                        problem_of_graph=prob, want_checks=True, free_out=free_buf, checks_out=checks_buf)
-        e3.record()
-        # per-problem result rows: (problem id, E_g, #collision-free edges, best logit) -> the only collective
-        rows = collision.result_rows(logits, free_buf, edge_ptr_d, rank * B, out=rows_buf)
-        if world > 1:
-            dist.all_gather_into_tensor(gather_buf.view(world * B, 4), rows)
-        state.update(et=et, edge_ptr=edge_ptr, rows=rows, ei=ei)
+    def step(timed=False):
+        evs = [ev() for _ in range(4)]
+        bufs = hp.compute(v_d, goal_d, obs_d, obs_ptr, prob_d, events=evs)
+        if world > 1:   # the only collective: per-problem result rows
+            dist.all_gather_into_tensor(gather_buf.view(world * B, 4), bufs["rows"])
+        state.update(et=bufs["et"], edge_ptr=bufs["edge_ptr"], rows=bufs["rows"], checks=bufs["checks"])
         if timed:
             torch.cuda.current_stream().synchronize()
             for k_, v_ in model.last_timings().items():
                 phase_ms[k_] = phase_ms.get(k_, 0.0) + v_
-            phase_ms["knn_graph"] = phase_ms.get("knn_graph", 0.0) + e0.elapsed_time(e1)
-            phase_ms["explorer_forward"] = phase_ms.get("explorer_forward", 0.0) + e1.elapsed_time(e2)
-            phase_ms["collision"] = phase_ms.get("collision", 0.0) + e2.elapsed_time(e3)
+            phase_ms["knn_graph"] = phase_ms.get("knn_graph", 0.0) + evs[0].elapsed_time(evs[1])
+            phase_ms["explorer_forward"] = phase_ms.get("explorer_forward", 0.0) + evs[1].elapsed_time(evs[2])
+            phase_ms["collision"] = phase_ms.get("collision", 0.0) + evs[2].elapsed_time(evs[3])
 
     def barrier():
         torch.cuda.synchronize()
@@ -315,12 +299,14 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed_region(fn, steps):
+    def timed_region(fn, steps, finish=None):
         barrier()
         a, b = ev(), ev()
         a.record()
         for _ in range(steps):
             fn()
+        if finish:
+            finish()
         b.record()
         barrier()
         ms = torch.tensor([a.elapsed_time(b)], device=dev)
@@ -330,36 +316,39 @@ def main():
 
     # ---- kernel-only: inputs resident in HBM
     for _ in range(args.warmup):
-        step(v_d, goal_d, obs_d, maps_d, prob_d)
+        step()
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    ms_step = timed_region(lambda: step(v_d, goal_d, obs_d, maps_d, prob_d, timed=True), args.steps)
+    ms_step = timed_region(lambda: step(timed=True), args.steps)
     clocks = sampler.stop() if sampler else None
     et = state["et"]
-    checks_total = int(checks_buf[:et].sum())
+    checks_total = int(state["checks"][:et].sum())
 
-    # ---- end to end: host (pinned) buffers in, host buffers out, copies inside the timed region
-    out_logits_h = torch.empty(cap, dtype=torch.float32).pin_memory()
-    out_free_h = torch.empty(cap, dtype=torch.uint8).pin_memory()
-    out_ei_h = torch.empty((2, cap), dtype=torch.int64).pin_memory()
-    in_bufs = [torch.empty_like(v_d), torch.empty_like(goal_d), torch.empty_like(obs_d), torch.empty_like(maps_d), torch.empty_like(prob_d)]
+    # ---- end to end through the public API: pinned host buffers in, pinned host buffers out, every step's
+    # host->device and device->host copies inside the timed region.  Results of step k are awaited (HotPath.wait) while
+    # step k+1 is already enqueued: the read-back runs on a second stream and overlaps the next step's kernels.
     io = {}
+    pending = []
 
     def e2e_step():
-        for d, h in zip(in_bufs, (v_h, goal_h, obs_h, maps_h, prob_h)):
-            d.copy_(h, non_blocking=True)
-        step(*in_bufs)
-        n = state["et"]
-        out_logits_h[:n].copy_(logits_buf[:n], non_blocking=True)
-        out_free_h[:n].copy_(free_buf[:n], non_blocking=True)
-        out_ei_h[0, :n].copy_(ei_buf[0, :n], non_blocking=True)   # two contiguous row copies
-        out_ei_h[1, :n].copy_(ei_buf[1, :n], non_blocking=True)
-        torch.cuda.current_stream().synchronize()   # the caller owns the results only after this
-        io["h2d"] = sum(h.numel() * h.element_size() for h in (v_h, goal_h, obs_h, maps_h, prob_h))
-        io["d2h"] = n * (4 + 1 + 16) + (B + 1) * 4
+        t = hp.submit(v_h, goal_h, obs_h, obs_ptr, prob_h, maps_h=maps_h if is_maze else None)
+        if world > 1:
+            dist.all_gather_into_tensor(gather_buf.view(world * B, 4), t["rows"])
+        pending.append(t)
+        if len(pending) > 1:
+            res = HotPath.wait(pending.pop(0))          # the host owns step k-1's results from here on
+            io["last_logit"] = float(res["logits"][0])
+        io["h2d"], io["d2h"] = t["h2d_bytes"], t["d2h_bytes"]
+
+    def e2e_finish():
+        while pending:
+            res = HotPath.wait(pending.pop(0))
+            io["last_logit"] = float(res["logits"][0])
+        torch.cuda.current_stream().synchronize()
 
     for _ in range(2):
         e2e_step()
-    ms_e2e = timed_region(e2e_step, args.steps)
+    e2e_finish()
+    ms_e2e = timed_region(e2e_step, args.steps, finish=e2e_finish)
 
     if rank != 0:
         if world > 1:
@@ -410,7 +399,8 @@ def main():
                                 "peak": hbm, "unit": "GB/s", "frac": msg_bytes / (msg_ms * 1e-3) / 1e9 / hbm, "traffic": None,
                                 "ms_per_launch": msg_ms},
         "e2e": {"value": B * world / (ms_e2e / 1000.0), "unit": "graphs/s", "h2d_bytes_per_step": io["h2d"], "d2h_bytes_per_step": io["d2h"],
-                "ms_per_step": ms_e2e},
+                "ms_per_step": ms_e2e, "api": "gnn_motion_planning_b200.batch.HotPath.submit/wait (double-buffered; read-back of "
+                                              "step k overlaps the kernels of step k+1)"},
         "gpu_launches": K * (5 + 3 + 1 + 1 + 1 + 1 + 6 + 5 + 1 + 1 + 1),
         "gpu_launches_note": "per step: knn 5 (select,row_count,row_scan,graph_scan,emit) + csr 3 + goal_index + obstacle + node_pre + "
                              "edge_feature + node_loop x6 + edge_msg x5 + policy + {maze,arm}_edge_graph + result_rows; memsets/copies not counted",

@@ -101,3 +101,38 @@ def test_str2name_factory(cuda_device):
     assert str2name("ur5", make_env=False)[3].scale == pytest.approx(2 * np.pi)
     with pytest.raises(KeyError):
         str2name("maze3", make_env=False)
+
+
+def test_hotpath_submit_wait_matches_compute(cuda_device):
+    """The public batched API: pinned-host submit/wait (double buffered, overlapped read-back) returns exactly what the
+    device-resident compute produces, batch after batch."""
+    from gnn_motion_planning_b200.batch import HotPath
+    from gnn_motion_planning_b200.model import EncoderProcessDecoder
+    dev = cuda_device
+    m = EncoderProcessDecoder(2, 2, 32, 2).to(dev)
+    m.load_state_dict(torch.load(os.path.join(G, "weights", "weights_maze.pt"), map_location="cpu"))
+    maps = np.load(os.path.join(G, "maze_maps_256.npz"))["maps"]
+    B, n, k = 6, 300, 12
+    hp = HotPath(m, B, n, k, kind="maze", maps=torch.from_numpy(maps).to(dev), first_problem_id=40, device=dev)
+    tickets, wants = [], []
+    for it in range(3):
+        rng = np.random.default_rng(it)
+        v = rng.uniform(-1, 1, (B * n, 2)).astype(np.float32)
+        obss = [(np.argwhere(maps[(it * B + g) % len(maps)] == 1) / 15.0 - 0.5).astype(np.float32) for g in range(B)]
+        obs_ptr = np.cumsum([0] + [len(o) for o in obss]).astype(np.int32)
+        v_h = torch.from_numpy(v).pin_memory()
+        goal_h = torch.from_numpy(v.reshape(B, n, 2)[:, 1].copy()).pin_memory()
+        obs_h = torch.from_numpy(np.concatenate(obss)).pin_memory()
+        prob_h = torch.from_numpy(((it * B + np.arange(B)) % len(maps)).astype(np.int32)).pin_memory()
+        bufs = hp.compute(v_h.to(dev), goal_h.to(dev), obs_h.to(dev), obs_ptr, prob_h.to(dev), bufs=hp._alloc_set())
+        et = bufs["et"]
+        wants.append((bufs["edge_ptr"].copy(), bufs["ei"][:, :et].cpu(), bufs["logits"][:et].cpu(), bufs["free"][:et].cpu(), bufs["rows"].cpu()))
+        tickets.append(hp.submit(v_h, goal_h, obs_h, obs_ptr, prob_h))
+        if it == 1:   # results of an older batch stay valid while newer ones are in flight (two buffer sets)
+            r0 = HotPath.wait(tickets[0])
+            assert torch.equal(r0["logits"], wants[0][2])
+    for t, (ep, ei, lg, fr, rows) in list(zip(tickets, wants))[1:]:
+        r = HotPath.wait(t)
+        assert np.array_equal(r["edge_ptr"], ep) and torch.equal(r["edge_index"], ei)
+        assert torch.equal(r["logits"], lg) and torch.equal(r["free"], fr) and torch.equal(r["rows"], rows)
+        assert float(rows[0, 0]) == 40.0

@@ -91,7 +91,7 @@ class ClockSampler:
         self.lines = []
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                       "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -208,7 +208,7 @@ os.dup2(2, 1)
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
@@ -367,6 +367,15 @@ def main():
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
+    traffic = {}
+    try:   # DRAM bytes per launch of the two named kernels, from the committed ncu --set full captures (C2 workload only)
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))) if args.workload == "C2" else {}
+    except Exception:
+        pass
+
+    def traffic_of(kernel):
+        t = traffic.get(kernel)
+        return (t["dram_bytes_read"] + t["dram_bytes_write"]) if t else None
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)"
     hbm = peaks.get("hbm_gbs", 6650.0)
@@ -391,12 +400,14 @@ def main():
         "knn_graphs_per_sec": B * world / (phase_ms["knn_graph"] / K / 1e3),
         "forward_tflops_ref_oplist": fwd_flops / (phase_ms["explorer_forward"] / K / 1e3) / 1e12,
         "roofline": {"kernel": "edge_feature_kernel<%d,%d>" % (c, wl["e"]), "bound": "tensor", "achieved": ef_tflops, "peak": peak_tf,
-                     "unit": "TFLOP/s", "frac": ef_tflops / peak_tf, "traffic": None, "peak_source": peak_src,
+                     "unit": "TFLOP/s", "frac": ef_tflops / peak_tf, "traffic": traffic_of("edge_feature_kernel<%d,%d>" % (c, wl["e"])),
+                     "peak_source": peak_src,
                      "ms_per_launch": ef_ms, "algorithmic_gflop_per_launch": ef_flops / 1e9,
                      "note": "fp32 FMA kernel (1e-4 logit tolerance rules out 1-pass TF32/BF16); vs fp32 SIMT peak "
                              "148 SM x 128 FMA x %.0f MHz = %.1f TFLOP/s the fraction is %.3f" % (sm_mhz, fp32_peak_tf, ef_tflops / fp32_peak_tf)},
         "roofline_hbm_kernel": {"kernel": "edge_msg_kernel<%d>" % wl["e"], "bound": "hbm", "achieved": msg_bytes / (msg_ms * 1e-3) / 1e9,
-                                "peak": hbm, "unit": "GB/s", "frac": msg_bytes / (msg_ms * 1e-3) / 1e9 / hbm, "traffic": None,
+                                "peak": hbm, "unit": "GB/s", "frac": msg_bytes / (msg_ms * 1e-3) / 1e9 / hbm,
+                                "traffic": traffic_of("edge_msg_kernel<%d>" % wl["e"]), "algorithmic_bytes_per_launch": msg_bytes,
                                 "ms_per_launch": msg_ms},
         "e2e": {"value": B * world / (ms_e2e / 1000.0), "unit": "graphs/s", "h2d_bytes_per_step": io["h2d"], "d2h_bytes_per_step": io["d2h"],
                 "ms_per_step": ms_e2e, "api": "gnn_motion_planning_b200.batch.HotPath.submit/wait (double-buffered; read-back of "

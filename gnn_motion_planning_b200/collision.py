@@ -90,7 +90,7 @@ def result_rows(logits, edge_free, edge_ptr_d, first_problem_id=0, out=None):
 
 
 # ------------------------------------------------------------------------------------------------ arms
-ARM_KUKA7, ARM_KUKA14, ARM_KUKA13 = 0, 1, 2
+ARM_KUKA7, ARM_KUKA14, ARM_KUKA13, ARM_UR5 = 0, 1, 2, 3
 
 
 def arm_model_info(model):
@@ -107,8 +107,8 @@ def pack_boxes(problems_obstacles, device):
     """list (per problem) of [(halfExtents[3], basePosition[3]), ...] -> (boxes [O_total,6] f64 cuda, box_ptr [P+1] i32 cuda)."""
     rows, ptr = [], [0]
     for obs in problems_obstacles:
-        for h, p in obs:
-            rows.append(np.concatenate([np.asarray(h, np.float64).reshape(3), np.asarray(p, np.float64).reshape(3)]))
+        for h, p in obs:   # ur5s_6_3000.pkl has ragged entries such as [0.01, 0.01, array([0.84])]
+            rows.append(np.array([float(np.ravel(x)[0]) for x in list(h) + list(p)], np.float64))
         ptr.append(len(rows))
     boxes = torch.from_numpy(np.array(rows, np.float64).reshape(-1, 6)).to(device)
     return boxes, torch.from_numpy(np.array(ptr, np.int32)).to(device)

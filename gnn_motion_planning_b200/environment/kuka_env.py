@@ -196,3 +196,16 @@ class Kuka2Env(KukaEnv):
         self._MODEL_OF_FILE = {kuka_file: collision.ARM_KUKA14}
         super().__init__(GUI=GUI, kuka_file=kuka_file, map_file=map_file, device=device, problems=problems)
         self.kukaEndEffectorIndex = 6
+
+
+class UR5Env(KukaEnv):
+    """reference environment/ur5_env.py: 6-DoF UR5 on a ground plane, self collision enabled, box obstacles."""
+    RRT_EPS = 0.1
+    voxel_r = 0.1
+
+    def __init__(self, GUI=False, map_file='maze_files/ur5s_6_3000.pkl', device=None, problems=None):
+        self._MODEL_OF_FILE = {"ur5/ur5.urdf": collision.ARM_UR5}
+        super().__init__(GUI=GUI, kuka_file="ur5/ur5.urdf", map_file=map_file, device=device, problems=problems)
+
+    def __str__(self):
+        return 'ur5'

@@ -1,10 +1,10 @@
 """Host-side mirror of reference ``str2name.py:11-81``: env-name -> (env, explorer, explorer-weights path, smoother,
-smoother-weights path[, data path]).  Same hyper-parameter table; models live on the GPU.  ``ur5`` and ``snake7``
-have explorer / smoother kernels but no collision model yet, so their env is ``None``."""
+smoother-weights path[, data path]).  Same hyper-parameter table; models live on the GPU.  ``snake7`` has explorer /
+smoother kernels but no collision model yet, so its env is ``None``."""
 import numpy as np
 import torch
 
-from .environment import Kuka2Env, KukaEnv, MazeEnv
+from .environment import Kuka2Env, KukaEnv, MazeEnv, UR5Env
 from .model import EncoderProcessDecoder
 from .model_smoother import ModelSmoother
 
@@ -28,7 +28,9 @@ def _make_env(name, **env_kwargs):
         return KukaEnv(kuka_file="kuka_iiwa/model_3.urdf", map_file=env_kwargs.pop("map_file", "maze_files/kukas_13_3000.pkl"), **env_kwargs)
     if name == "kuka14":
         return Kuka2Env(**env_kwargs)
-    return None   # ur5 / snake7: collision model not implemented on the B200 path yet
+    if name == "ur5":
+        return UR5Env(**env_kwargs)
+    return None   # snake7: collision model not implemented on the B200 path yet
 
 
 def str2name(str, get_data=False, use_obstacle=True, load=False, make_env=True, **env_kwargs):

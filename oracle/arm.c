@@ -24,12 +24,26 @@
 #include "../gnn_motion_planning_b200/csrc/arm_models_data.h"
 #include "../include/gmp_arm_math.h"
 
-typedef struct { int n_arms, dof_per_arm, n_spheres; const GmpJoint* joints; const GmpSphere* spheres; double base_x[2]; } ArmModel;
+typedef struct {
+  int n_arms, dof_per_arm, n_spheres;
+  const GmpJoint* joints;
+  const GmpSphere* spheres;
+  double base_x[2];
+  int self_collision;      /* URDF_USE_SELF_COLLISION (ur5_env.py:107): links not directly connected may collide */
+  int plane_exempt_frame;  /* ground plane z = 0 (ur5_env.py:108-111), -2 = no plane; this frame's link is filtered out */
+} ArmModel;
 
 static ArmModel get_model(int id) {
   ArmModel m;
   m.base_x[0] = m.base_x[1] = 0.0;
-  if (id == GMP_ARM_KUKA13) {
+  m.self_collision = 0;
+  m.plane_exempt_frame = -2;
+  if (id == GMP_ARM_UR5) {
+    m.n_arms = 1; m.dof_per_arm = 6; m.joints = gmp_ur5_joints; m.spheres = gmp_ur5_spheres;
+    m.n_spheres = (int)(sizeof(gmp_ur5_spheres) / sizeof(GmpSphere));
+    m.self_collision = 1;
+    m.plane_exempt_frame = 0;
+  } else if (id == GMP_ARM_KUKA13) {
     m.n_arms = 1; m.dof_per_arm = 13; m.joints = gmp_kuka13_joints; m.spheres = gmp_kuka13_spheres;
     m.n_spheres = (int)(sizeof(gmp_kuka13_spheres) / sizeof(GmpSphere));
   } else {
@@ -98,6 +112,23 @@ static int config_collides(const ArmModel* m, const double* q, const double* box
         if (d2 <= rr * rr) return 1;
       }
     }
+  if (m->plane_exempt_frame != -2)
+    for (int s = 0; s < m->n_spheres; ++s) {
+      if (m->spheres[s].frame == m->plane_exempt_frame) continue;
+      if (w[0][3 * s + 2] <= m->spheres[s].r + GMP_ARM_MARGIN) return 1;
+    }
+  if (m->self_collision)
+    for (int s = 0; s < m->n_spheres; ++s)
+      for (int t = s + 1; t < m->n_spheres; ++t) {
+        if (m->spheres[t].frame - m->spheres[s].frame < 2) continue; /* same link or directly connected links */
+        const double rr = (m->spheres[s].r + m->spheres[t].r) + GMP_ARM_MARGIN;
+        double d2 = 0.0;
+        for (int i = 0; i < 3; ++i) {
+          const double d = w[0][3 * s + i] - w[0][3 * t + i];
+          d2 = d2 + d * d;
+        }
+        if (d2 <= rr * rr) return 1;
+      }
   if (m->n_arms == 2)
     for (int s = 0; s < m->n_spheres; ++s)
       for (int t = 0; t < m->n_spheres; ++t) {

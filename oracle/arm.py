@@ -7,7 +7,7 @@ import numpy as np
 
 from .maze import lib
 
-KUKA7, KUKA14, KUKA13 = 0, 1, 2
+KUKA7, KUKA14, KUKA13, UR5 = 0, 1, 2, 3
 
 
 def _ptr(a):
@@ -29,8 +29,8 @@ def pack_boxes(problems_obstacles):
     """list (per problem) of [(halfExtents[3], basePosition[3]), ...] -> (boxes [O_total,6] f64, box_ptr [P+1] i32)."""
     rows, ptr = [], [0]
     for obs in problems_obstacles:
-        for h, p in obs:
-            rows.append(np.concatenate([np.asarray(h, np.float64), np.asarray(p, np.float64)]))
+        for h, p in obs:   # ur5s_6_3000.pkl has ragged entries such as [0.01, 0.01, array([0.84])]
+            rows.append(np.array([float(np.ravel(x)[0]) for x in list(h) + list(p)], np.float64))
         ptr.append(len(rows))
     return np.array(rows, np.float64).reshape(-1, 6), np.array(ptr, np.int32)
 

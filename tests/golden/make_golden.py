@@ -71,6 +71,7 @@ def sym_knn_edges(v, k):
 
 
 def main():
+    np.random.seed(20211206)   # MazeEnv.sample_n_points draws from the global NumPy RNG: keep the fixtures reproducible
     os.chdir(REF)  # MazeEnv opens 'maze_files/...' relative to cwd
     sys.path.insert(0, REF)
     MazeEnv = load_ref_maze_env()
@@ -225,16 +226,17 @@ def main():
     # for the arm model (PyBullet itself cannot run here: arm parity is unpinned).
     import pickle
     arm = {}
-    for tag, fn in (("kuka7", "kukas_7_3000.pkl"), ("kuka14", "kukas_14_3000.pkl"), ("kuka13", "kukas_13_3000.pkl")):
+    for tag, fn in (("kuka7", "kukas_7_3000.pkl"), ("kuka14", "kukas_14_3000.pkl"), ("kuka13", "kukas_13_3000.pkl"),
+                    ("ur5", "ur5s_6_3000.pkl")):
         with open(os.path.join(REF, "maze_files", fn), "rb") as f:
             pr = pickle.load(f)[:48]
         boxes, ptr, known, known_p, ea, eb, ep = [], [0], [], [], [], [], []
         for i, (obs, st, go, path) in enumerate(pr):
-            for h, b in obs:
-                boxes.append(np.concatenate([h, b]))
+            for h, b in obs:   # ur5 entries are ragged, e.g. [0.01, 0.01, array([0.84])]
+                boxes.append(np.array([float(np.ravel(x)[0]) for x in list(h) + list(b)]))
             ptr.append(len(boxes))
             for q in [st, go] + list(path):
-                known.append(np.asarray(q, np.float64)); known_p.append(i)
+                known.append(np.asarray(q, np.float64).reshape(-1)); known_p.append(i)
             path = np.asarray(path, np.float64)
             for u, w in zip(path[:-1], path[1:]):
                 ea.append(u); eb.append(w); ep.append(i)

@@ -9,7 +9,7 @@ import pytest
 from oracle import arm
 
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-MODELS = [("kuka7", arm.KUKA7, 7), ("kuka14", arm.KUKA14, 14), ("kuka13", arm.KUKA13, 13)]
+MODELS = [("kuka7", arm.KUKA7, 7), ("kuka14", arm.KUKA14, 14), ("kuka13", arm.KUKA13, 13), ("ur5", arm.UR5, 6)]
 
 
 @pytest.fixture(scope="module")
@@ -26,10 +26,10 @@ def test_known_free_states(probs, tag, model, dof):
     free, counted = arm.state_fp(model, probs[tag + "_known_free"], probs[tag + "_boxes"], probs[tag + "_box_ptr"],
                                  probs[tag + "_known_free_problem"])
     assert counted.all()
-    assert free.mean() >= {"kuka7": 0.999, "kuka14": 0.95, "kuka13": 0.97}[tag], free.mean()
+    assert free.mean() >= {"kuka7": 0.999, "kuka14": 0.95, "kuka13": 0.97, "ur5": 0.999}[tag], free.mean()
     fe, ce = arm.edge_fp(model, probs[tag + "_path_a"], probs[tag + "_path_b"], probs[tag + "_boxes"], probs[tag + "_box_ptr"],
-                         probs[tag + "_path_problem"], rrt_eps=0.5)
-    assert fe.mean() >= {"kuka7": 0.999, "kuka14": 0.95, "kuka13": 0.97}[tag], fe.mean()
+                         probs[tag + "_path_problem"], rrt_eps=0.1 if tag == "ur5" else 0.5)
+    assert fe.mean() >= {"kuka7": 0.999, "kuka14": 0.95, "kuka13": 0.97, "ur5": 0.999}[tag], fe.mean()
     assert (ce[fe == 1] >= 2).all()
 
 
@@ -84,3 +84,14 @@ def test_sincos_spec():
         for x in np.linspace(-7, 7, 2001):
             lib.sc(ctypes.c_double(x), ctypes.byref(s), ctypes.byref(c))
             assert abs(s.value - math.sin(x)) < 4e-16 and abs(c.value - math.cos(x)) < 4e-16
+
+
+def test_ur5_self_collision_and_plane():
+    """UR5Env (ur5_env.py:107-111): self collision between links that are not directly connected, ground plane z = 0."""
+    none = (np.zeros((0, 6)), np.array([0, 0], np.int32))
+    up = np.array([[0.0, -np.pi / 2, 0.0, -np.pi / 2, 0.0, 0.0]])          # arm pointing straight up: free
+    assert arm.state_fp(arm.UR5, up, *none)[0][0] == 1
+    down = np.array([[0.0, np.pi / 2, 0.0, 0.0, 0.0, 0.0]])                # upper arm pointing into the ground
+    assert arm.state_fp(arm.UR5, down, *none)[0][0] == 0
+    folded = np.array([[0.0, -np.pi / 2, np.pi, 0.0, 0.0, 0.0]])           # forearm folded back through the upper arm / shoulder
+    assert arm.state_fp(arm.UR5, folded, *none)[0][0] == 0

@@ -133,6 +133,58 @@ def chain_from_urdf(urdf, mesh_dir):
     return J, spheres
 
 
+def tree_chain_from_urdf(urdf, skip_links=()):
+    """General URDF tree with fixed joints (ur5.urdf): the revolute joints along the path root -> tip become the chain;
+    fixed joints are folded into the next revolute joint's origin (or, after the last one, into the sphere centres).
+    Frame 0 = everything rigidly attached to the root, frame k = child side of the k-th revolute joint."""
+    root = ET.parse(urdf).getroot()
+    links = {l.get("name"): l for l in root.findall("link")}
+    joints = root.findall("joint")
+    children = {}
+    for j in joints:
+        children.setdefault(j.find("parent").get("link"), []).append(j)
+    child_names = {j.find("child").get("link") for j in joints}
+    base = [n for n in links if n not in child_names][0]
+
+    def origin_of(el):
+        o = el.find("origin")
+        xyz = [float(x) for x in (o.get("xyz") if o is not None and o.get("xyz") else "0 0 0").split()]
+        rpy = [float(x) for x in (o.get("rpy") if o is not None and o.get("rpy") else "0 0 0").split()]
+        return rpy_matrix(*rpy), np.array(xyz)
+
+    J, spheres = [], []
+
+    def visit(link, frame, R, t):      # (R, t): pose of `link` in its movable frame
+        col = links[link].find("collision")
+        if col is not None and link not in skip_links:
+            mesh = col.find("geometry").find("mesh")
+            if mesh is not None:
+                Rm, tm = origin_of(col)
+                pts = read_stl(os.path.join(os.path.dirname(urdf), mesh.get("filename"))) @ Rm.T + tm
+                pts = pts @ R.T + t
+                c, r = fit_spheres(pts, K_SPHERES)
+                for ci, ri in zip(c, r):
+                    spheres.append((frame, ci, ri))
+                print("  %-18s frame %d %6d verts -> %d inscribed spheres, radii %.3f..%.3f, hull volume covered %.0f%%" % (
+                    link, frame, len(pts), len(c), r.min(), r.max(), 100 * fit_spheres.last_coverage))
+        for j in children.get(link, []):
+            Rj, tj = origin_of(j)
+            Rc, tc = R @ Rj, R @ tj + t
+            child = j.find("child").get("link")
+            if j.get("type") == "revolute":
+                lim = j.find("limit")
+                axis = np.array([float(x) for x in j.find("axis").get("xyz").split()])
+                J.append(dict(R=Rc, t=tc, axis=axis, lo=float(lim.get("lower")), hi=float(lim.get("upper"))))
+                assert len(J) == frame + 1, "branching kinematic trees are not handled"
+                visit(child, frame + 1, np.eye(3), np.zeros(3))
+            else:
+                visit(child, frame, Rc, tc)
+
+    visit(base, 0, np.eye(3), np.zeros(3))
+    spheres.sort(key=lambda s: s[0])
+    return J, spheres
+
+
 def emit_model(f, name, J, spheres):
     f.write("static const GmpJoint %s_joints[] = {\n" % name)
     for j in J:
@@ -151,6 +203,8 @@ def main():
     models["kuka7"] = chain_from_urdf(os.path.join(REF, "kuka_iiwa/model_0.urdf"), os.path.join(REF, "kuka_iiwa"))
     print("kuka13 <- kuka_iiwa/model_3.urdf")
     models["kuka13"] = chain_from_urdf(os.path.join(REF, "kuka_iiwa/model_3.urdf"), os.path.join(REF, "kuka_iiwa"))
+    print("ur5 <- ur5/ur5.urdf")
+    models["ur5"] = tree_chain_from_urdf(os.path.join(REF, "ur5/ur5.urdf"), skip_links=("ee_link",))
     with open(OUT, "w") as f:
         f.write("// GENERATED by tools/make_arm_models.py from the reference's URDF + STL assets -- data only.\n"
                 "// Shared by csrc/arm.cu (the kernel) and oracle/arm.c (its checker): the geometric SPEC of the arm model.\n"
@@ -162,8 +216,10 @@ def main():
         for name, (J, S) in models.items():
             emit_model(f, "gmp_" + name, J, S)
         f.write("// model ids: 0 = kuka7 (KukaEnv, kuka_env.py), 1 = kuka14 (Kuka2Env: two kuka7 chains based at x = -0.5 / +0.5,\n"
-                "// kuka_2arm_env.py:58-59, arm-arm contacts included), 2 = kuka13 (KukaEnv with model_3.urdf)\n"
-                "#define GMP_ARM_KUKA7 0\n#define GMP_ARM_KUKA14 1\n#define GMP_ARM_KUKA13 2\n#define GMP_ARM_NUM_MODELS 3\n")
+                "// kuka_2arm_env.py:58-59, arm-arm contacts included), 2 = kuka13 (KukaEnv with model_3.urdf),\n"
+                "// 3 = ur5 (UR5Env, ur5_env.py:104-127: self collision between links that are not directly connected, ground plane z = 0\n"
+                "// except for the base link; the 1 cm ee_link box is dropped)\n"
+                "#define GMP_ARM_KUKA7 0\n#define GMP_ARM_KUKA14 1\n#define GMP_ARM_KUKA13 2\n#define GMP_ARM_UR5 3\n#define GMP_ARM_NUM_MODELS 4\n")
     print("wrote", OUT)
 
 

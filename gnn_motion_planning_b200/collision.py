@@ -90,7 +90,7 @@ def result_rows(logits, edge_free, edge_ptr_d, first_problem_id=0, out=None):
 
 
 # ------------------------------------------------------------------------------------------------ arms
-ARM_KUKA7, ARM_KUKA14, ARM_KUKA13, ARM_UR5 = 0, 1, 2, 3
+ARM_KUKA7, ARM_KUKA14, ARM_KUKA13, ARM_UR5, ARM_SNAKE7 = 0, 1, 2, 3, 4
 
 
 def arm_model_info(model):
@@ -112,6 +112,15 @@ def pack_boxes(problems_obstacles, device):
         ptr.append(len(rows))
     boxes = torch.from_numpy(np.array(rows, np.float64).reshape(-1, 6)).to(device)
     return boxes, torch.from_numpy(np.array(ptr, np.int32)).to(device)
+
+
+def snake_obstacles(maps):
+    """SnakeEnv.create_maze (snake_env.py:63-71): half extents (0.7, 0.7, 1) at (1.4 i - 10.5, 1.4 j - 10.5, 0) for every
+    occupied cell map[i, j], reference loop order (j outer, i inner) -> list (per problem) of (half, pos) pairs."""
+    out = []
+    for m in np.asarray(maps):
+        out.append([((0.7, 0.7, 1.0), (1.4 * i - 10.5, 1.4 * j - 10.5, 0.0)) for j in range(m.shape[0]) for i in range(m.shape[1]) if m[i, j]])
+    return out
 
 
 @torch.no_grad()

@@ -209,3 +209,59 @@ class UR5Env(KukaEnv):
 
     def __str__(self):
         return 'ur5'
+
+
+class SnakeEnv(KukaEnv):
+    """reference environment/snake_env.py: 7-D planar snake (base x, y + 5 angles, of which config[3] drives both the
+    base yaw and joint 3 and config[6] is unused -- snake_env.py:124-128) in a maze of boxes, self collision enabled."""
+    RRT_EPS = 0.1
+    voxel_r = 0.1
+    height = 0.5
+
+    def __init__(self, map_file='maze_files/snakes_15_2_3000.npz', GUI=False, device=None, maps=None, init_states=None,
+                 goal_states=None):
+        if GUI:
+            raise NotImplementedError("no GUI on the B200 path")
+        if maps is None:
+            with np.load(map_file) as f:
+                maps, init_states, goal_states = f['maps'], f['init_states'], f['goal_states']
+        self.maps, self.init_states, self.goal_states = maps, init_states, goal_states
+        self.dim = 2
+        self._model = collision.ARM_SNAKE7
+        self.collision_check_count = 0
+        self.size = self.maps.shape[0]
+        self.width = self.maps.shape[1]
+        self.episode_i = 0
+        self.order = list(range(self.size))
+        self.collision_point = None
+        self.device = torch.device(device if device is not None else "cuda")
+        self.config_dim, lo, hi = collision.arm_model_info(self._model)
+        self.pose_range = [(float(a), float(b)) for a, b in zip(lo, hi)]       # snake_env.py:55
+        self.bound = np.array(self.pose_range).T.reshape(-1)
+        self._boxes, self._box_ptr = collision.pack_boxes(collision.snake_obstacles(self.maps), self.device)
+        self._problem = 0
+        self.k = 0
+
+    def __str__(self):
+        return 'snake' + str(self.config_dim)
+
+    def init_new_problem(self, index=None):
+        if index is None:
+            index = self.episode_i
+        self.episode_i += 1
+        self.episode_i = self.episode_i % len(self.order)
+        self.collision_check_count = 0
+        self._problem = index
+        self.map = self.maps[index]
+        occ = np.argwhere(self.map == 1)
+        self.obstacles = occ / self.map.shape[0] - 0.5          # snake_env.py:148-152
+        self.collision_point = None
+        self.init_state = self.init_states[index]
+        self.goal_state = self.goal_states[index]
+        return self.get_problem()
+
+    def get_problem(self):
+        return {"map": self.map, "init_state": self.init_state, "goal_state": self.goal_state}
+
+    def get_robot_points(self, config):
+        return np.array(config[:2])

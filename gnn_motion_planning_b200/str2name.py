@@ -1,10 +1,9 @@
 """Host-side mirror of reference ``str2name.py:11-81``: env-name -> (env, explorer, explorer-weights path, smoother,
-smoother-weights path[, data path]).  Same hyper-parameter table; models live on the GPU.  ``snake7`` has explorer /
-smoother kernels but no collision model yet, so its env is ``None``."""
+smoother-weights path[, data path]).  Same hyper-parameter table; models live on the GPU."""
 import numpy as np
 import torch
 
-from .environment import Kuka2Env, KukaEnv, MazeEnv, UR5Env
+from .environment import Kuka2Env, KukaEnv, MazeEnv, SnakeEnv, UR5Env
 from .model import EncoderProcessDecoder
 from .model_smoother import ModelSmoother
 
@@ -30,7 +29,9 @@ def _make_env(name, **env_kwargs):
         return Kuka2Env(**env_kwargs)
     if name == "ur5":
         return UR5Env(**env_kwargs)
-    return None   # snake7: collision model not implemented on the B200 path yet
+    if name == "snake7":
+        return SnakeEnv(**env_kwargs)
+    return None
 
 
 def str2name(str, get_data=False, use_obstacle=True, load=False, make_env=True, **env_kwargs):

@@ -26,6 +26,9 @@
 
 typedef struct {
   int n_arms, dof_per_arm, n_spheres;
+  int n_joints;            /* chain length per arm (== dof_per_arm except for the snake's planar base) */
+  int self_min_diff;       /* self collision between links whose frames differ by at least this much */
+  double lo[GMP_ARM_MAX_JOINTS], hi[GMP_ARM_MAX_JOINTS]; /* limits of the STATE components of one arm */
   const GmpJoint* joints;
   const GmpSphere* spheres;
   double base_x[2];
@@ -37,8 +40,15 @@ static ArmModel get_model(int id) {
   ArmModel m;
   m.base_x[0] = m.base_x[1] = 0.0;
   m.self_collision = 0;
+  m.self_min_diff = 2;
   m.plane_exempt_frame = -2;
-  if (id == GMP_ARM_UR5) {
+  if (id == GMP_ARM_SNAKE7) {
+    /* snake_env.py:90: URDF_USE_SELF_COLLISION | URDF_USE_SELF_COLLISION_INCLUDE_PARENT */
+    m.n_arms = 1; m.dof_per_arm = 7; m.joints = gmp_snake7_joints; m.spheres = gmp_snake7_spheres;
+    m.n_spheres = (int)(sizeof(gmp_snake7_spheres) / sizeof(GmpSphere));
+    m.self_collision = 1;
+    m.self_min_diff = 1;
+  } else if (id == GMP_ARM_UR5) {
     m.n_arms = 1; m.dof_per_arm = 6; m.joints = gmp_ur5_joints; m.spheres = gmp_ur5_spheres;
     m.n_spheres = (int)(sizeof(gmp_ur5_spheres) / sizeof(GmpSphere));
     m.self_collision = 1;
@@ -51,6 +61,11 @@ static ArmModel get_model(int id) {
     m.n_spheres = (int)(sizeof(gmp_kuka7_spheres) / sizeof(GmpSphere));
     if (id == GMP_ARM_KUKA14) { m.base_x[0] = -0.5; m.base_x[1] = 0.5; }
   }
+  m.n_joints = m.dof_per_arm;
+  for (int j = 0; j < m.dof_per_arm; ++j) {
+    m.lo[j] = id == GMP_ARM_SNAKE7 ? gmp_snake7_lo[j] : m.joints[j].lo;
+    m.hi[j] = id == GMP_ARM_SNAKE7 ? gmp_snake7_hi[j] : m.joints[j].hi;
+  }
   return m;
 }
 
@@ -59,33 +74,40 @@ int oracle_arm_dof(int id) { ArmModel m = get_model(id); return m.n_arms * m.dof
 void oracle_arm_limits(int id, double* lo, double* hi) {
   ArmModel m = get_model(id);
   for (int a = 0; a < m.n_arms; ++a)
-    for (int j = 0; j < m.dof_per_arm; ++j) { lo[a * m.dof_per_arm + j] = m.joints[j].lo; hi[a * m.dof_per_arm + j] = m.joints[j].hi; }
+    for (int j = 0; j < m.dof_per_arm; ++j) { lo[a * m.dof_per_arm + j] = m.lo[j]; hi[a * m.dof_per_arm + j] = m.hi[j]; }
 }
 
 /* world sphere centres of one arm: out[3 * s] */
 static void arm_spheres_world(const ArmModel* m, const double* q, double base_x, double* out) {
   double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, p[3] = {base_x, 0.0, 0.0};
   int s = 0;
-  for (int f = 0; f <= m->dof_per_arm; ++f) {
+  for (int f = 0; f <= m->n_joints; ++f) {
     if (f > 0) {
       const GmpJoint* J = &m->joints[f - 1];
+      const double qj = q[J->qidx];
       /* p += R * t ; R = R * Rj */
       double np_[3], R1[9], Rq[9], R2[9];
       for (int i = 0; i < 3; ++i) np_[i] = p[i] + ((R[3 * i] * J->t[0] + R[3 * i + 1] * J->t[1]) + R[3 * i + 2] * J->t[2]);
       for (int i = 0; i < 3; ++i)
         for (int k = 0; k < 3; ++k)
           R1[3 * i + k] = (R[3 * i] * J->R[k] + R[3 * i + 1] * J->R[3 + k]) + R[3 * i + 2] * J->R[6 + k];
-      double sn, cs;
-      gmp_sincos(q[f - 1], &sn, &cs);
-      const double ax = J->axis[0], ay = J->axis[1], az = J->axis[2], oc = 1.0 - cs;
-      Rq[0] = cs + oc * (ax * ax); Rq[1] = oc * (ax * ay) - sn * az; Rq[2] = oc * (ax * az) + sn * ay;
-      Rq[3] = oc * (ay * ax) + sn * az; Rq[4] = cs + oc * (ay * ay); Rq[5] = oc * (ay * az) - sn * ax;
-      Rq[6] = oc * (az * ax) - sn * ay; Rq[7] = oc * (az * ay) + sn * ax; Rq[8] = cs + oc * (az * az);
-      for (int i = 0; i < 3; ++i)
-        for (int k = 0; k < 3; ++k)
-          R2[3 * i + k] = (R1[3 * i] * Rq[k] + R1[3 * i + 1] * Rq[3 + k]) + R1[3 * i + 2] * Rq[6 + k];
-      for (int i = 0; i < 9; ++i) R[i] = R2[i];
-      for (int i = 0; i < 3; ++i) p[i] = np_[i];
+      if (J->type == 1) { /* prismatic: translate along the joint axis, orientation unchanged */
+        const double v0 = J->axis[0] * qj, v1 = J->axis[1] * qj, v2 = J->axis[2] * qj;
+        for (int i = 0; i < 3; ++i) p[i] = np_[i] + ((R1[3 * i] * v0 + R1[3 * i + 1] * v1) + R1[3 * i + 2] * v2);
+        for (int i = 0; i < 9; ++i) R[i] = R1[i];
+      } else {
+        double sn, cs;
+        gmp_sincos(qj, &sn, &cs);
+        const double ax = J->axis[0], ay = J->axis[1], az = J->axis[2], oc = 1.0 - cs;
+        Rq[0] = cs + oc * (ax * ax); Rq[1] = oc * (ax * ay) - sn * az; Rq[2] = oc * (ax * az) + sn * ay;
+        Rq[3] = oc * (ay * ax) + sn * az; Rq[4] = cs + oc * (ay * ay); Rq[5] = oc * (ay * az) - sn * ax;
+        Rq[6] = oc * (az * ax) - sn * ay; Rq[7] = oc * (az * ay) + sn * ax; Rq[8] = cs + oc * (az * az);
+        for (int i = 0; i < 3; ++i)
+          for (int k = 0; k < 3; ++k)
+            R2[3 * i + k] = (R1[3 * i] * Rq[k] + R1[3 * i + 1] * Rq[3 + k]) + R1[3 * i + 2] * Rq[6 + k];
+        for (int i = 0; i < 9; ++i) R[i] = R2[i];
+        for (int i = 0; i < 3; ++i) p[i] = np_[i];
+      }
     }
     while (s < m->n_spheres && m->spheres[s].frame == f) {
       const double* c = m->spheres[s].c;
@@ -120,7 +142,7 @@ static int config_collides(const ArmModel* m, const double* q, const double* box
   if (m->self_collision)
     for (int s = 0; s < m->n_spheres; ++s)
       for (int t = s + 1; t < m->n_spheres; ++t) {
-        if (m->spheres[t].frame - m->spheres[s].frame < 2) continue; /* same link or directly connected links */
+        if (m->spheres[t].frame - m->spheres[s].frame < m->self_min_diff) continue; /* same / (ur5) directly connected links */
         const double rr = (m->spheres[s].r + m->spheres[t].r) + GMP_ARM_MARGIN;
         double d2 = 0.0;
         for (int i = 0; i < 3; ++i) {
@@ -147,7 +169,7 @@ static int state_valid(const ArmModel* m, const double* q) {
   for (int a = 0; a < m->n_arms; ++a)
     for (int j = 0; j < m->dof_per_arm; ++j) {
       const double x = q[a * m->dof_per_arm + j];
-      if (!(x >= m->joints[j].lo && x <= m->joints[j].hi)) return 0;
+      if (!(x >= m->lo[j] && x <= m->hi[j])) return 0;
     }
   return 1;
 }

@@ -7,7 +7,7 @@ import numpy as np
 
 from .maze import lib
 
-KUKA7, KUKA14, KUKA13, UR5 = 0, 1, 2, 3
+KUKA7, KUKA14, KUKA13, UR5, SNAKE7 = 0, 1, 2, 3, 4
 
 
 def _ptr(a):
@@ -58,3 +58,12 @@ def edge_fp(model, a, b, boxes, box_ptr, problem=None, rrt_eps=0.5):
                                                  _ptr(np.ascontiguousarray(box_ptr, np.int32)), _ptr(problem),
                                                  ctypes.c_int64(n), ctypes.c_double(rrt_eps), _ptr(free), _ptr(cnt))
     return free, cnt
+
+
+def snake_boxes(maps):
+    """SnakeEnv.create_maze (snake_env.py:63-71): a box of half extents (0.7, 0.7, 1) at (1.4 i - 10.5, 1.4 j - 10.5, 0) for
+    every occupied cell map[i, j], in the reference's loop order (j outer, i inner)."""
+    obs = []
+    for m in np.asarray(maps):
+        obs.append([((0.7, 0.7, 1.0), (1.4 * i - 10.5, 1.4 * j - 10.5, 0.0)) for j in range(m.shape[0]) for i in range(m.shape[1]) if m[i, j]])
+    return pack_boxes(obs)

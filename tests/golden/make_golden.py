@@ -245,6 +245,8 @@ def main():
                     tag + "_path_a": np.array(ea), tag + "_path_b": np.array(eb), tag + "_path_problem": np.array(ep, np.int32),
                     tag + "_start": np.array([p[1] for p in pr]), tag + "_goal": np.array([p[2] for p in pr])})
         print("arm problems", tag, len(boxes), "boxes,", len(known), "known-free states")
+    with np.load(os.path.join(REF, "maze_files", "snakes_15_2_3000.npz")) as f:     # snake: maps + PyBullet-free init / goal states
+        arm.update({"snake7_maps": f["maps"][:48].astype(np.uint8), "snake7_start": f["init_states"][:48], "snake7_goal": f["goal_states"][:48]})
     np.savez_compressed(os.path.join(HERE, "arm_problems.npz"), **arm)
 
     # ---------------------------------------------------------------- end-to-end explore() golden: BASELINE config C1

@@ -103,3 +103,47 @@ def test_kuka_env_protocol(cuda_device, probs):
         of, oc = o_arm.edge_fp(model, a[None], b[None], boxes, ptr, np.array([2], np.int32), rrt_eps=0.5)
         assert got == bool(of[0]) and env.collision_check_count - c0 == oc[0]
         assert env._state_fp(np.asarray(env.init_state)) in (True, False)
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_snake_vs_oracle(cuda_device, probs, dt):
+    from gnn_motion_planning_b200 import collision
+    from oracle import arm as o_arm
+    maps = probs["snake7_maps"]
+    boxes, ptr = o_arm.snake_boxes(maps)
+    bd, pd = collision.pack_boxes(collision.snake_obstacles(maps), cuda_device)
+    assert np.array_equal(bd.cpu().numpy(), boxes) and np.array_equal(pd.cpu().numpy(), ptr)
+    d, lo, hi = collision.arm_model_info(collision.ARM_SNAKE7)
+    assert d == 7
+    rng = np.random.default_rng(8)
+    n = 40000
+    q = rng.uniform(lo * 1.01, hi * 1.01, (n, 7)).astype(dt)
+    prob = rng.integers(0, len(maps), n).astype(np.int32)
+    free, counted = collision.arm_state_fp(collision.ARM_SNAKE7, torch.from_numpy(q).to(cuda_device), bd, pd,
+                                           torch.from_numpy(prob).to(cuda_device), want_counted=True)
+    of, oc = o_arm.state_fp(o_arm.SNAKE7, q, boxes, ptr, prob)
+    assert np.array_equal(free.cpu().numpy(), of) and np.array_equal(counted.cpu().numpy(), oc)
+    assert 0.03 < of.mean() < 0.5
+    m = 15000
+    a = rng.uniform(lo, hi, (m, 7)).astype(dt)
+    b = np.clip(a + rng.normal(0, 0.15, (m, 7)), lo, hi).astype(dt)
+    free, checks = collision.arm_edge_fp(collision.ARM_SNAKE7, torch.from_numpy(a).to(cuda_device), torch.from_numpy(b).to(cuda_device),
+                                         bd, pd, torch.from_numpy(prob[:m]).to(cuda_device), rrt_eps=0.1, want_checks=True)
+    of, oc = o_arm.edge_fp(o_arm.SNAKE7, a, b, boxes, ptr, prob[:m], rrt_eps=0.1)
+    assert np.array_equal(free.cpu().numpy(), of) and np.array_equal(checks.cpu().numpy(), oc)
+
+
+def test_snake_and_ur5_env(cuda_device, probs):
+    from gnn_motion_planning_b200.environment import SnakeEnv, UR5Env
+    env = SnakeEnv(maps=probs["snake7_maps"].astype(np.float64), init_states=probs["snake7_start"], goal_states=probs["snake7_goal"])
+    assert str(env) == "snake7" and env.config_dim == 7 and env.RRT_EPS == 0.1
+    env.init_new_problem(3)
+    assert env._state_fp(np.asarray(env.init_state)) and env._state_fp(np.asarray(env.goal_state))
+    assert env.collision_check_count == 2 and env.obstacles.shape[1] == 2
+    boxes, ptr = probs["ur5_boxes"], probs["ur5_box_ptr"]
+    problems = [([(boxes[j, :3], boxes[j, 3:]) for j in range(ptr[i], ptr[i + 1])], probs["ur5_start"][i], probs["ur5_goal"][i], [])
+                for i in range(len(ptr) - 1)]
+    u = UR5Env(problems=problems)
+    assert str(u) == "ur5" and u.config_dim == 6 and u.RRT_EPS == 0.1 and abs(np.max(u.bound) - 2 * np.pi) < 1e-9
+    u.init_new_problem(5)
+    assert u._state_fp(np.asarray(u.init_state, dtype=np.float64)) and u.in_goal_region(np.asarray(u.goal_state, dtype=np.float64))

@@ -95,3 +95,21 @@ def test_ur5_self_collision_and_plane():
     assert arm.state_fp(arm.UR5, down, *none)[0][0] == 0
     folded = np.array([[0.0, -np.pi / 2, np.pi, 0.0, 0.0, 0.0]])           # forearm folded back through the upper arm / shoulder
     assert arm.state_fp(arm.UR5, folded, *none)[0][0] == 0
+
+
+def test_snake_model(probs):
+    """SnakeEnv: all dataset init / goal states (free under PyBullet) are free; the config[3] double use and the unused
+    config[6] of snake_env.py:124-128 are reproduced; a folded snake collides with itself."""
+    boxes, ptr = arm.snake_boxes(probs["snake7_maps"])
+    n = len(probs["snake7_start"])
+    S = np.concatenate([probs["snake7_start"], probs["snake7_goal"]])
+    free, counted = arm.state_fp(arm.SNAKE7, S, boxes, ptr, np.concatenate([np.arange(n), np.arange(n)]))
+    assert counted.all() and free.all()
+    none = (np.zeros((0, 6)), np.array([0, 0], np.int32))
+    q = np.array([[0.0, 0.0, 0.3, -0.2, 0.4, 0.1, 0.0]])
+    q2 = q.copy(); q2[0, 6] = 2.5                        # config[6] is never read
+    assert arm.state_fp(arm.SNAKE7, q, *none)[0][0] == 1 and arm.state_fp(arm.SNAKE7, q2, *none)[0][0] == 1
+    fold = np.array([[0.0, 0.0, 3.0, 0.0, 0.0, 0.0, 0.0]])   # first joint folded back by ~172 degrees: link 1 lies on the shoulder link
+    assert arm.state_fp(arm.SNAKE7, fold, *none)[0][0] == 0
+    lo, hi = arm.limits(arm.SNAKE7)
+    assert lo[0] == -9 and hi[1] == 9 and abs(hi[2] - np.pi) < 1e-15

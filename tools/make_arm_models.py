@@ -185,12 +185,42 @@ def tree_chain_from_urdf(urdf, skip_links=()):
     return J, spheres
 
 
+def snake_model():
+    """environment/snake.urdf + SnakeEnv.set_config (snake_env.py:118-135): a planar free base (x, y at height 0.5, yaw) and
+    four revolute z joints; links are spheres (r 0.08) and capsules (length 0.44, r 0.05, axis = local y).  Capsules are
+    filled with inscribed spheres along their axis.  Reference quirk kept: yaw AND joint 3 both read config[3], config[6]
+    is unused (qidx below)."""
+    root = ET.parse(os.path.join(REF, "environment/snake.urdf")).getroot()
+    radii = {l.get("name"): l.find("collision").find("geometry") for l in root.findall("link")}
+    ball_r = float(radii["ball_0"].find("sphere").get("radius"))
+    cap = radii["link_1"].find("capsule")
+    cap_len, cap_r = float(cap.get("length")), float(cap.get("radius"))
+    seg = float(root.find("joint").find("origin").get("xyz").split()[1])          # -0.4: every joint steps -0.4 in y
+    eye = np.eye(3)
+    J = [dict(R=eye, t=np.array([0, 0, 0.5]), axis=np.array([1.0, 0, 0]), lo=-9.0, hi=9.0, type=1, qidx=0),   # base x (SnakeEnv.height)
+         dict(R=eye, t=np.zeros(3), axis=np.array([0, 1.0, 0]), lo=-9.0, hi=9.0, type=1, qidx=1),              # base y
+         dict(R=eye, t=np.zeros(3), axis=np.array([0, 0, 1.0]), lo=-np.pi, hi=np.pi, type=0, qidx=3)]          # base yaw <- config[3]
+    spheres = []
+
+    def add_block(frame):        # ball at the frame origin, capsule centred one step further along -y
+        spheres.append((frame, np.zeros(3), ball_r))
+        n = 9
+        for y in np.linspace(-cap_len / 2, cap_len / 2, n):
+            spheres.append((frame, np.array([0.0, seg + y, 0.0]), cap_r))
+
+    add_block(3)
+    for k, qi in enumerate((2, 3, 4, 5)):      # joints 1,3,5,7 <- config[2..5]   (snake_env.py:127-128)
+        J.append(dict(R=eye, t=np.array([0.0, 2 * seg, 0.0]), axis=np.array([0, 0, 1.0]), lo=-np.pi, hi=np.pi, type=0, qidx=qi))
+        add_block(4 + k)
+    return J, spheres
+
+
 def emit_model(f, name, J, spheres):
     f.write("static const GmpJoint %s_joints[] = {\n" % name)
-    for j in J:
+    for idx, j in enumerate(J):
         Rt = ", ".join("%.17g" % x for x in j["R"].reshape(-1))
-        f.write("  {{%s}, {%.17g, %.17g, %.17g}, {%.17g, %.17g, %.17g}, %.17g, %.17g},\n" % (
-            Rt, *j["t"], *j["axis"], j["lo"], j["hi"]))
+        f.write("  {{%s}, {%.17g, %.17g, %.17g}, {%.17g, %.17g, %.17g}, %.17g, %.17g, %d, %d},\n" % (
+            Rt, *j["t"], *j["axis"], j["lo"], j["hi"], j.get("type", 0), j.get("qidx", idx)))
     f.write("};\nstatic const GmpSphere %s_spheres[] = {\n" % name)
     for fi, c, r in spheres:
         f.write("  {%d, {%.17g, %.17g, %.17g}, %.17g},\n" % (fi, *c, r))
@@ -205,12 +235,15 @@ def main():
     models["kuka13"] = chain_from_urdf(os.path.join(REF, "kuka_iiwa/model_3.urdf"), os.path.join(REF, "kuka_iiwa"))
     print("ur5 <- ur5/ur5.urdf")
     models["ur5"] = tree_chain_from_urdf(os.path.join(REF, "ur5/ur5.urdf"), skip_links=("ee_link",))
+    print("snake7 <- environment/snake.urdf")
+    models["snake7"] = snake_model()
     with open(OUT, "w") as f:
         f.write("// GENERATED by tools/make_arm_models.py from the reference's URDF + STL assets -- data only.\n"
                 "// Shared by csrc/arm.cu (the kernel) and oracle/arm.c (its checker): the geometric SPEC of the arm model.\n"
                 "// Joint chain: frame 0 = base link; frame j+1 = frame j * [R|t]_j * Rot(axis_j, q_j).\n"
                 "#pragma once\n\n"
-                "typedef struct { double R[9]; double t[3]; double axis[3]; double lo, hi; } GmpJoint;\n"
+                "// type: 0 = revolute about `axis`, 1 = prismatic along `axis`; qidx = which state component drives the joint\n"
+                "typedef struct { double R[9]; double t[3]; double axis[3]; double lo, hi; int type, qidx; } GmpJoint;\n"
                 "typedef struct { int frame; double c[3]; double r; } GmpSphere;\n"
                 "#define GMP_ARM_MARGIN %.17g\n#define GMP_ARM_MAX_JOINTS 14\n#define GMP_ARM_MAX_SPHERES 176\n\n" % MARGIN)
         for name, (J, S) in models.items():
@@ -219,7 +252,12 @@ def main():
                 "// kuka_2arm_env.py:58-59, arm-arm contacts included), 2 = kuka13 (KukaEnv with model_3.urdf),\n"
                 "// 3 = ur5 (UR5Env, ur5_env.py:104-127: self collision between links that are not directly connected, ground plane z = 0\n"
                 "// except for the base link; the 1 cm ee_link box is dropped)\n"
-                "#define GMP_ARM_KUKA7 0\n#define GMP_ARM_KUKA14 1\n#define GMP_ARM_KUKA13 2\n#define GMP_ARM_UR5 3\n#define GMP_ARM_NUM_MODELS 4\n")
+                "// 4 = snake7 (SnakeEnv, snake_env.py: planar base + 4 joints, self collision incl. directly connected links; state limits\n"
+                "// (-9,9)^2 x (-pi,pi)^5 from snake_env.py:55; the ground plane never touches a robot riding at z = 0.5)\n"
+                "#define GMP_ARM_KUKA7 0\n#define GMP_ARM_KUKA14 1\n#define GMP_ARM_KUKA13 2\n#define GMP_ARM_UR5 3\n#define GMP_ARM_SNAKE7 4\n"
+                "#define GMP_ARM_NUM_MODELS 5\n"
+                "static const double gmp_snake7_lo[7] = {-9, -9, %.17g, %.17g, %.17g, %.17g, %.17g};\n"
+                "static const double gmp_snake7_hi[7] = {9, 9, %.17g, %.17g, %.17g, %.17g, %.17g};\n" % ((-np.pi,) * 5 + (np.pi,) * 5))
     print("wrote", OUT)
 
 

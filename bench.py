@@ -34,6 +34,15 @@ WORKLOADS = {
     "C2": dict(env="maze2", c=2, e=32, s=2, ws=2, n=1000, k=50, batch=256, weights="weights_maze.pt", lo=-1.0, hi=1.0),
     "C3": dict(env="kuka7", c=7, e=64, s=6, ws=3, n=1000, k=50, batch=256, weights="weights_kuka.pt", lo=-2.9, hi=2.9),
     "C4": dict(env="kuka14", c=14, e=32, s=6, ws=3, n=2000, k=50, batch=128, weights="kuka_14.pt", lo=-2.9, hi=2.9),
+    # C5 = BASELINE.json configs[4]: mixed env sweep, 256 problems per GPU split over the five environments
+    "C5": dict(env="mixed", parts=[("maze2", 52), ("snake7", 51), ("ur5", 51), ("kuka7", 51), ("kuka14", 51)], n=1000, k=50, batch=256),
+}
+PARTS = {
+    "maze2": dict(env="maze2", c=2, e=32, s=2, ws=2, weights="weights_maze.pt", lo=-1.0, hi=1.0),
+    "snake7": dict(env="snake7", c=7, e=32, s=2, ws=3, weights="weights_snake.pt"),
+    "ur5": dict(env="ur5", c=6, e=32, s=6, ws=3, weights="weights_ur5.pt"),
+    "kuka7": dict(env="kuka7", c=7, e=64, s=6, ws=3, weights="weights_kuka.pt"),
+    "kuka14": dict(env="kuka14", c=14, e=32, s=6, ws=3, weights="kuka_14.pt"),
 }
 
 
@@ -60,13 +69,165 @@ _AP = {}
 ARM_LIMITS = {"kuka7": (np.array([-2.96705972839, -2.09439510239, -2.96705972839, -2.09439510239, -2.96705972839, -2.09439510239, -3.05432619099]),
                         np.array([2.96705972839, 2.09439510239, 2.96705972839, 2.09439510239, 2.96705972839, 2.09439510239, 3.05432619099]))}
 ARM_LIMITS["kuka14"] = (np.tile(ARM_LIMITS["kuka7"][0], 2), np.tile(ARM_LIMITS["kuka7"][1], 2))
-ARM_MODEL = {"kuka7": 0, "kuka14": 1}
+ARM_LIMITS["ur5"] = (np.array([-2 * np.pi, -2 * np.pi, -np.pi, -2 * np.pi, -2 * np.pi, -2 * np.pi]),
+                     np.array([2 * np.pi, 2 * np.pi, np.pi, 2 * np.pi, 2 * np.pi, 2 * np.pi]))
+ARM_LIMITS["snake7"] = (np.array([-9, -9] + [-np.pi] * 5), np.array([9, 9] + [np.pi] * 5))
+ARM_MODEL = {"kuka7": 0, "kuka14": 1, "ur5": 3, "snake7": 4}
+ARM_EPS = {"kuka7": 0.5, "kuka14": 0.5, "ur5": 0.1, "snake7": 0.1}
 
 
 def _arm_problems():
     if "d" not in _AP:
         _AP["d"] = np.load(os.path.join(G, "arm_problems.npz"))
     return _AP["d"]
+
+
+def run_mixed(args, wl, rank, local_rank, world):
+    """BASELINE.json configs[4]: mixed environment sweep.  Every rank runs one HotPath per environment over its share of the
+    problems; a step = all five sub-batches (graph build + forward + all-edge collision check each)."""
+    import torch
+    import torch.distributed as dist
+    from gnn_motion_planning_b200 import _lib, collision
+    from gnn_motion_planning_b200.batch import HotPath
+    from gnn_motion_planning_b200.model import EncoderProcessDecoder
+    _lib.load()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    ap = _arm_problems()
+    maps_np = np.load(os.path.join(G, "maze_maps_256.npz"))["maps"]
+    N, k = wl["n"], wl["k"]
+    subs = []
+    first = rank * wl["batch"]
+    for env, B in wl["parts"]:
+        pw = PARTS[env]
+        model = EncoderProcessDecoder(workspace_size=pw["ws"], config_size=pw["c"], embed_size=pw["e"], obs_size=pw["s"]).to(dev)
+        model.load_state_dict(torch.load(os.path.join(G, "weights", pw["weights"]), map_location="cpu"))
+        model.set_timing(True)
+        vs, obss, probs = [], [], []
+        for g in range(B):
+            rng = np.random.default_rng(1234 + first + g)
+            if env == "maze2":
+                vs.append(rng.uniform(-1, 1, (N, 2)).astype(np.float32))
+                pi = (first + g) % len(maps_np)
+                obss.append((np.argwhere(maps_np[pi] == 1) / 15.0 - 0.5).astype(np.float32))
+            else:
+                lo, hi = ARM_LIMITS[env]
+                vs.append(rng.uniform(lo, hi, (N, pw["c"])).astype(np.float32))
+                if env == "snake7":
+                    pi = (first + g) % len(ap["snake7_maps"])
+                    obss.append((np.argwhere(ap["snake7_maps"][pi] == 1) / 15.0 - 0.5).astype(np.float32))
+                else:
+                    ptr = ap[env + "_box_ptr"]
+                    pi = (first + g) % (len(ptr) - 1)
+                    obss.append(ap[env + "_boxes"][ptr[pi]:ptr[pi + 1]].astype(np.float32))
+            probs.append(pi)
+        if env == "maze2":
+            hp = HotPath(model, B, N, k, kind="maze", maps=torch.from_numpy(maps_np).to(dev), first_problem_id=first, device=dev)
+        else:
+            if env == "snake7":
+                boxes_d, ptr_d = collision.pack_boxes(collision.snake_obstacles(ap["snake7_maps"]), dev)
+            else:
+                boxes_d, ptr_d = torch.from_numpy(ap[env + "_boxes"]).to(dev), torch.from_numpy(ap[env + "_box_ptr"]).to(dev)
+            hp = HotPath(model, B, N, k, kind="arm", boxes=boxes_d, box_ptr=ptr_d, arm_model=ARM_MODEL[env], rrt_eps=ARM_EPS[env],
+                         first_problem_id=first, device=dev)
+        first += B
+        v_h = torch.from_numpy(np.concatenate(vs)).pin_memory()
+        subs.append(dict(env=env, B=B, hp=hp, model=model, v_h=v_h, goal_h=torch.from_numpy(np.stack([x[1] for x in vs])).pin_memory(),
+                         obs_h=torch.from_numpy(np.concatenate(obss)).pin_memory(),
+                         obs_ptr=np.cumsum([0] + [len(o) for o in obss]).astype(np.int32),
+                         prob_h=torch.from_numpy(np.array(probs, np.int32)).pin_memory()))
+    for s in subs:
+        s["dev_in"] = [s[k_].to(dev) for k_ in ("v_h", "goal_h", "obs_h", "prob_h")]
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    per_env_ms, edges, checks = {}, {}, {}
+
+    def step(timed=False):
+        for s in subs:
+            a, b = ev(), ev()
+            a.record()
+            bufs = s["hp"].compute(s["dev_in"][0], s["dev_in"][1], s["dev_in"][2], s["obs_ptr"], s["dev_in"][3])
+            b.record()
+            if world > 1:
+                dist.all_gather_into_tensor(s.setdefault("gather", torch.empty((world * s["B"], 4), device=dev)), bufs["rows"])
+            if timed:
+                b.synchronize()
+                per_env_ms[s["env"]] = per_env_ms.get(s["env"], 0.0) + a.elapsed_time(b)
+                edges[s["env"]] = bufs["et"]
+                checks[s["env"]] = int(bufs["checks"][:bufs["et"]].sum())
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_region(fn, steps, finish=None):
+        barrier()
+        a, b = ev(), ev()
+        a.record()
+        for _ in range(steps):
+            fn()
+        if finish:
+            finish()
+        b.record()
+        barrier()
+        ms = torch.tensor([a.elapsed_time(b)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / steps
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms_step = timed_region(lambda: step(True), args.steps)
+    clocks = sampler.stop() if sampler else None
+    pending, io = [], {"h2d": 0, "d2h": 0}
+
+    def e2e_step():
+        io["h2d"] = io["d2h"] = 0
+        for s in subs:
+            t = s["hp"].submit(s["v_h"], s["goal_h"], s["obs_h"], s["obs_ptr"], s["prob_h"])
+            pending.append(t)
+            io["h2d"] += t["h2d_bytes"]
+            io["d2h"] += t["d2h_bytes"]
+        while len(pending) > len(subs):
+            HotPath.wait(pending.pop(0))
+
+    def e2e_finish():
+        while pending:
+            HotPath.wait(pending.pop(0))
+
+    for _ in range(2):
+        e2e_step()
+    e2e_finish()
+    ms_e2e = timed_region(e2e_step, args.steps, finish=e2e_finish)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    K = args.steps
+    Btot = wl["batch"]
+    line = {
+        "metric": "explorer_graphs_per_sec", "value": Btot * world / (ms_step / 1e3), "unit": "graphs/s", "n_gpus": world, "steps": K,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "C5: mixed env sweep %s, %d-node k=%d RGG, loop=5, shipped weights" % (wl["parts"], N, k),
+                   "step": "per environment: knn_graph + explorer_forward + edge collision check of all edges",
+                   "global_batch": Btot * world, "parallelism": "dp%d" % world, "l2": "working set >> 126 MB L2"},
+        "per_env_ms_per_step": {k_: v_ / K for k_, v_ in per_env_ms.items()},
+        "per_env_edges": edges, "per_env_state_checks_per_edge": {k_: checks[k_] / max(edges[k_], 1) for k_ in edges},
+        "roofline": None, "cpu_baseline": None,
+        "e2e": {"value": Btot * world / (ms_e2e / 1e3), "unit": "graphs/s", "h2d_bytes_per_step": io["h2d"], "d2h_bytes_per_step": io["d2h"],
+                "ms_per_step": ms_e2e},
+        "gpu_launches": K * len(subs) * 27, "clocks": clocks,
+        "note": "mixed sweep: roofline / cpu_baseline are reported by the single-environment workloads (C2, C3, C4)",
+    }
+    _emit(line)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def ref_oplist_flops(n, e_cnt, o, c, e, s, loop=5):
@@ -222,6 +383,13 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
+    if args.workload == "C5":
+        if args.impl == "reference":
+            if rank == 0:
+                _emit({"impl": "reference", "unavailable": "mixed sweep: run --workload C2/C3/C4 for the per-environment CPU port baseline"})
+            return
+        run_mixed(args, wl, rank, local_rank, world)
+        return
     if args.impl == "reference":
         run_reference(args, wl, rank, world)
         return

@@ -81,7 +81,8 @@ def main():
     # ---------------------------------------------------------------- weights (binary fixtures)
     wdir = os.path.join(HERE, "weights")
     os.makedirs(wdir, exist_ok=True)
-    for w in ("weights_maze.pt", "weights_kuka.pt", "kuka_14.pt", "smooth_2d_attv3.pt", "smooth_7d_attv3.pt"):
+    for w in ("weights_maze.pt", "weights_kuka.pt", "kuka_14.pt", "weights_snake.pt", "weights_ur5.pt", "smooth_2d_attv3.pt",
+              "smooth_7d_attv3.pt"):
         shutil.copyfile(os.path.join(REF, "data/weights", w), os.path.join(wdir, w))
 
     # ---------------------------------------------------------------- maze problems subset

@@ -10,7 +10,8 @@
 
 ``compute`` runs one batch from device-resident inputs.  ``submit`` / ``wait`` are the end-to-end path: inputs come
 from pinned host buffers, results (edge_index, logits, free flags, edge_ptr) are delivered into pinned host buffers;
-two device/host buffer sets and a copy stream let the read-back of batch k overlap the kernels of batch k+1.
+two device/host buffer sets and three streams (graph build | forward + collision | read-back) keep the GPU busy
+across batches.
 """
 import numpy as np
 import torch
@@ -33,6 +34,7 @@ class HotPath:
         self.cap = int(self.B * _lib.load().gmp_knn_graph_max_edges(self.N, self.k))
         self.sets = [self._alloc_set() for _ in range(2)]
         self.copy_stream = torch.cuda.Stream(device=self.dev)
+        self.graph_stream = torch.cuda.Stream(device=self.dev)
         self._k = 0
 
     def _alloc_set(self):
@@ -44,25 +46,22 @@ class HotPath:
         return s
 
     # ------------------------------------------------------------------ one batch, device-resident inputs
-    def compute(self, v, goal, obstacles, obs_ptr, problem_of_graph, bufs=None, events=None):
-        """v [B*N,c] f32, goal [B,c], obstacles [O_total,s], obs_ptr host [B+1], problem_of_graph [B] i32 (device).
-        Fills bufs (edge_index, logits, free, checks, rows); returns bufs.  `events`: optional 4 CUDA events recorded at
-        the phase boundaries (graph build | forward | collision)."""
-        bufs = bufs if bufs is not None else self.sets[0]
-        if events:
-            events[0].record()
+    def _build_graphs(self, v, bufs):
         ei, edge_ptr = graph.knn_graph_batch(v, self.node_ptr, self.n_free, self.k1, edge_index_out=bufs["ei"])  # syncs: B+1 ints
-        if events:
-            events[1].record()
-        et = int(edge_ptr[-1])
+        bufs["et"], bufs["edge_ptr"] = int(edge_ptr[-1]), edge_ptr
+        return ei
+
+    def _score_and_check(self, v, goal, obstacles, obs_ptr, problem_of_graph, bufs, maps=None, events=None):
+        ei, edge_ptr, et = bufs["ei"], bufs["edge_ptr"], bufs["et"]
         logits = self.model.forward_batch(v, ei, goal, obstacles, self.node_ptr, edge_ptr, obs_ptr, loop=self.loop, dense=False,
                                           out=bufs["logits"])
         if events:
             events[2].record()
         edge_ptr_d = torch.from_numpy(edge_ptr).to(self.dev, non_blocking=True)
         if self.kind == "maze":
-            collision.maze_edge_fp_graph(v, ei, self.node_ptr_d, edge_ptr_d, self.maps, et, problem_of_graph=problem_of_graph,
-                                         want_checks=True, free_out=bufs["free"], checks_out=bufs["checks"])
+            collision.maze_edge_fp_graph(v, ei, self.node_ptr_d, edge_ptr_d, maps if maps is not None else self.maps, et,
+                                         problem_of_graph=problem_of_graph, want_checks=True, free_out=bufs["free"],
+                                         checks_out=bufs["checks"])
         else:
             collision.arm_edge_fp_graph(self.arm_model, v, ei, self.node_ptr_d, edge_ptr_d, self.boxes, self.box_ptr, et,
                                         rrt_eps=self.rrt_eps, problem_of_graph=problem_of_graph, want_checks=True,
@@ -70,7 +69,18 @@ class HotPath:
         if events:
             events[3].record()
         collision.result_rows(logits, bufs["free"], edge_ptr_d, self.first_problem_id, out=bufs["rows"])
-        bufs["et"], bufs["edge_ptr"] = et, edge_ptr
+
+    def compute(self, v, goal, obstacles, obs_ptr, problem_of_graph, bufs=None, events=None):
+        """v [B*N,c] f32, goal [B,c], obstacles [O_total,s], obs_ptr host [B+1], problem_of_graph [B] i32 (device).
+        Fills bufs (edge_index, logits, free, checks, rows) on the current stream; returns bufs.  `events`: optional 4 CUDA
+        events recorded at the phase boundaries (graph build | forward | collision)."""
+        bufs = bufs if bufs is not None else self.sets[0]
+        if events:
+            events[0].record()
+        self._build_graphs(v, bufs)
+        if events:
+            events[1].record()
+        self._score_and_check(v, goal, obstacles, obs_ptr, problem_of_graph, bufs, events=events)
         return bufs
 
     # ------------------------------------------------------------------ end to end: pinned host in, pinned host out
@@ -80,27 +90,36 @@ class HotPath:
                     free=pin(self.cap, dtype=torch.uint8), rows=pin((self.B, 4), dtype=torch.float32))
 
     def submit(self, v_h, goal_h, obs_h, obs_ptr, prob_h, maps_h=None):
-        """Enqueue one batch from PINNED host tensors; returns a ticket for ``wait``.  Host->device copies, kernels and
-        the device->host read-back of the results are all issued here; the read-back runs on a second stream so it
-        overlaps the next batch's kernels."""
+        """Enqueue one batch from PINNED host tensors; returns a ticket for ``wait``.  Three streams form a pipeline over
+        two buffer sets: host->device copies + graph build of batch k+1 (graph stream) run while the forward / collision
+        kernels of batch k occupy the main stream, and the device->host read-back of batch k (copy stream) overlaps both.
+        The only host synchronisation is the B+1-int edge_ptr read-back of the graph build, which waits for the graph
+        stream only -- the main stream never drains."""
         s = self.sets[self._k % 2]
         self._k += 1
         if s["host"] is None:
             s["host"] = self._host_set()
             s["inputs"] = [None, None, None, None]
+            s["graph_done"] = torch.cuda.Event()
+            s["maps_d"] = torch.empty_like(self.maps) if (self.kind == "maze" and maps_h is not None) else None
         main = torch.cuda.current_stream(self.dev)
-        main.wait_event(s["copy_done"])                       # the previous read-back of this buffer set has finished
-        staged = []
-        for i, h in enumerate((v_h, goal_h, obs_h, prob_h)):   # device staging buffers grow on demand (ragged obstacle counts)
-            d = s["inputs"][i]
-            if d is None or d.shape[0] < h.shape[0] or d.shape[1:] != h.shape[1:] or d.dtype != h.dtype:
-                d = s["inputs"][i] = torch.empty((max(h.shape[0], 1),) + tuple(h.shape[1:]), dtype=h.dtype, device=self.dev)
-            d = d[:h.shape[0]]
-            d.copy_(h, non_blocking=True)
-            staged.append(d)
-        if maps_h is not None:                                # the occupancy maps are per-problem inputs too
-            self.maps.copy_(maps_h, non_blocking=True)
-        self.compute(staged[0], staged[1], staged[2], obs_ptr, staged[3], bufs=s)
+        gs = self.graph_stream
+        gs.wait_event(s["copy_done"])                         # the previous read-back of this buffer set has finished
+        with torch.cuda.stream(gs):
+            staged = []
+            for i, h in enumerate((v_h, goal_h, obs_h, prob_h)):   # device staging buffers grow on demand (ragged obstacle counts)
+                d = s["inputs"][i]
+                if d is None or d.shape[0] < h.shape[0] or d.shape[1:] != h.shape[1:] or d.dtype != h.dtype:
+                    d = s["inputs"][i] = torch.empty((max(h.shape[0], 1),) + tuple(h.shape[1:]), dtype=h.dtype, device=self.dev)
+                d = d[:h.shape[0]]
+                d.copy_(h, non_blocking=True)
+                staged.append(d)
+            if s["maps_d"] is not None:                       # the occupancy maps are per-problem inputs too
+                s["maps_d"].copy_(maps_h, non_blocking=True)
+            self._build_graphs(staged[0], s)
+            s["graph_done"].record(gs)
+        main.wait_event(s["graph_done"])
+        self._score_and_check(staged[0], staged[1], staged[2], obs_ptr, staged[3], s, maps=s["maps_d"])
         s["compute_done"].record(main)
         n = s["et"]
         with torch.cuda.stream(self.copy_stream):

@@ -23,6 +23,7 @@ SIGNATURES = {
     "gmp_explorer_init": (c_int, [c_void_p, c_int, c_int, c_int]),
     "gmp_explorer_set_tensor": (c_int, [c_void_p, c_char_p, c_void_p, c_int64]),
     "gmp_explorer_finalize": (c_int, [c_void_p]),
+    "gmp_explorer_set_edge_feature_mode": (c_int, [c_void_p, c_int]),
     "gmp_explorer_workspace_bytes": (c_int64, [c_void_p, c_int64, c_int64, c_int64, c_int64]),
     "gmp_explorer_forward": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),

@@ -34,6 +34,7 @@
 
 #include "handle.h"
 #include "rowtile.cuh"
+#include "explorer_tc.cuh"
 
 namespace gmp {
 namespace {
@@ -918,6 +919,39 @@ std::vector<double> transpose_window(const std::vector<float>& W, int out, int i
 
 struct Spec { const char* name; int64_t numel; };
 
+// round-to-nearest (ties away) TF32 of an fp32 value, as cvt.rna.tf32.f32
+float tf32_rna_host(float x) {
+  uint32_t u;
+  std::memcpy(&u, &x, 4);
+  u = (u + 0x1000u) & 0xFFFFE000u;
+  std::memcpy(&x, &u, 4);
+  return x;
+}
+
+// B[n][k] (N x K) -> [hi plane | lo plane] for the tensor-core kernels; a plane is float[KP/4][N][4] (K-major,
+// no swizzle), K zero padded to KP (umma.cuh)
+void put_planes(Packer& pk, const std::vector<double>& B, int N, int K, int KP) {
+  std::vector<float> hi((size_t)N * KP, 0.f), lo((size_t)N * KP, 0.f);
+  for (int n = 0; n < N; ++n)
+    for (int k = 0; k < K; ++k) {
+      const float w = (float)B[(size_t)n * K + k];
+      const float h = tf32_rna_host(w);
+      const size_t i = ((size_t)(k / 4) * N + n) * 4 + (k % 4);
+      hi[i] = h;
+      lo[i] = tf32_rna_host(w - h);
+    }
+  pk.put(hi);
+  pk.put(lo);
+}
+
+// rows [r0, r0 + n) x columns [c0, c0 + k) of a torch Linear weight W [out][in] as doubles
+std::vector<double> window(const std::vector<float>& W, int in, int r0, int n, int c0, int k) {
+  std::vector<double> t((size_t)n * k);
+  for (int a = 0; a < n; ++a)
+    for (int b = 0; b < k; ++b) t[(size_t)a * k + b] = W[(size_t)(r0 + a) * in + c0 + b];
+  return t;
+}
+
 }  // namespace
 
 int explorer_build_image(ExplorerModel& m) {
@@ -1067,6 +1101,51 @@ int explorer_build_image(ExplorerModel& m) {
     w.goal_enc = pk.begin();
     pk.put(ge);
   }
+  // ---- tensor-core image of the edge-feature stage (e = 32): hi / lo TF32 planes in the order of TcCfg<C>
+  w.tc_img = -1;
+  if (e == 32) {
+    const int k0 = (2 * c + 7) / 8 * 8;
+    w.tc_img = pk.begin();
+    put_planes(pk, window(T("edge_free_code.0.weight"), 2 * c, 0, e, 0, 2 * c), e, 2 * c, k0);
+    put_planes(pk, window(T("edge_free_code.2.weight"), e, 0, e, 0, e), e, e, e);
+    put_planes(pk, window(T("edge_code.0.weight"), 2 * c, 0, e, 0, 2 * c), e, 2 * c, k0);
+    put_planes(pk, window(T("edge_code.2.weight"), e, 0, e, 0, e), e, e, e);
+    for (int i = 0; i < 3; ++i) {
+      const std::string p = "edge_attentions." + std::to_string(i) + ".";
+      const auto& Wq = T(p + "attention.query.weight");
+      const auto& Wk = T(p + "attention.key.weight");
+      const auto& Wv = T(p + "attention.value.weight");
+      std::vector<double> GV((size_t)2 * e * e);   // rows 0..e-1: G[a][b]; rows e..2e-1: Wv[n][k]
+      for (int a = 0; a < e; ++a)
+        for (int b = 0; b < e; ++b) {
+          double sum = 0;
+          for (int o = 0; o < e; ++o) sum += (double)Wq[(size_t)o * e + a] * (double)Wk[(size_t)o * e + b];
+          GV[(size_t)a * e + b] = scale * sum;
+          GV[(size_t)(e + a) * e + b] = Wv[(size_t)a * e + b];
+        }
+      put_planes(pk, GV, 2 * e, e, e);
+      put_planes(pk, window(T(p + "map_feed.w_1.weight"), e, 0, e, 0, e), e, e, e);
+      put_planes(pk, window(T(p + "map_feed.w_2.weight"), e, 0, e, 0, e), e, e, e);
+    }
+    {
+      const auto& Wp = T("policy.0.weight");
+      const auto& W0 = T("process.lin_0.0.weight");
+      std::vector<double> QP = window(Wp, 3 * e, 0, e, 2 * e, e), Pef = window(W0, 5 * e, 0, e, 3 * e, e);
+      QP.insert(QP.end(), Pef.begin(), Pef.end());
+      put_planes(pk, QP, 2 * e, e, e);
+      put_planes(pk, window(W0, 5 * e, 0, e, 4 * e, e), e, e, e);
+    }
+    pk.put(T("edge_free_code.0.bias")); pk.put(T("edge_free_code.2.bias"));
+    pk.put(T("edge_code.0.bias")); pk.put(T("edge_code.2.bias"));
+    for (int i = 0; i < 3; ++i) {
+      const std::string p = "edge_attentions." + std::to_string(i) + ".";
+      pk.put(T(p + "attention.layer_norm.weight")); pk.put(T(p + "attention.layer_norm.bias"));
+      pk.put(T(p + "map_feed.w_1.bias")); pk.put(T(p + "map_feed.w_2.bias"));
+      pk.put(T(p + "map_feed.layer_norm.weight")); pk.put(T(p + "map_feed.layer_norm.bias"));
+    }
+    pk.put(T("policy.0.bias"));
+    pk.put(T("process.lin_0.0.bias"));
+  }
   pk.begin();
   for (int q = 0; q < 4 * e + 64; ++q) pk.buf.push_back(0.f);  // slack: stages may over-read up to a few vectors
   if (m.d_weights) cudaFree(m.d_weights);
@@ -1088,9 +1167,11 @@ struct ExWs {
   int64_t* dense_off;
   int32_t *indeg, *in_ptr, *cursor, *csr_src, *csr_dst, *csr_eid;
   float *tables, *X0, *D0, *H, *Xg, *AGG, *A, *B, *P, *Q;
+  int64_t* tc_tab_off;   // tensor-core edge-feature stage: per-graph float offset of its obstacle-table units
+  float* tc_tables;      // 3 blocks x tc_rows x 128 floats (hi / lo planes of M and V per 96-obstacle chunk)
 };
 
-int64_t carve_explorer(Carver& cv, ExWs& ws, int e, int64_t B, int64_t Nt, int64_t Et, int64_t obs_tiles) {
+int64_t carve_explorer(Carver& cv, ExWs& ws, int e, int64_t B, int64_t Nt, int64_t Et, int64_t obs_tiles, int64_t tc_rows) {
   const int ot = (e == 32) ? 32 : 16;
   ws.node_ptr = cv.take<int32_t>(B + 1);
   ws.edge_ptr = cv.take<int32_t>(B + 1);
@@ -1116,6 +1197,8 @@ int64_t carve_explorer(Carver& cv, ExWs& ws, int e, int64_t B, int64_t Nt, int64
   ws.B = cv.take<float>(Nt * e);
   ws.P = cv.take<float>(Et * e);
   ws.Q = cv.take<float>(Et * e);
+  ws.tc_tab_off = cv.take<int64_t>(B + 1);
+  ws.tc_tables = cv.take<float>(3 * tc_rows * 4 * e);
   return cv.bytes();
 }
 
@@ -1149,9 +1232,19 @@ int run_forward(gmp_handle* h, int64_t B, const float* v, const int64_t* edge_in
     dense_off[g + 1] = dense_off[g] + n * n;
   }
   const int64_t obs_tiles = obs_tile_ptr[B];
+  // tensor-core edge-feature stage (e = 32): obstacle-table units of tc_per() rows per chunk
+  const bool use_tc = E == 32 && m.w.tc_img >= 0 && m.edge_feature_mode != 0;
+  std::vector<int64_t> tc_off(B + 1, 0);
+  if (use_tc)
+    for (int64_t g = 0; g < B; ++g) {
+      const int no = obs_ptr[g + 1] - obs_ptr[g];
+      const int nch = tc_nchunks(no);
+      tc_off[g + 1] = tc_off[g] + (int64_t)nch * tc_per(no, nch) * 4 * E;
+    }
+  const int64_t tc_rows = tc_off[B] / (4 * E);
   Carver cv(workspace);
   ExWs ws;
-  const int64_t need = carve_explorer(cv, ws, E, B, Nt, Et, obs_tiles);
+  const int64_t need = carve_explorer(cv, ws, E, B, Nt, Et, obs_tiles, tc_rows);
   GMP_REQUIRE(need <= workspace_bytes, "workspace too small (see gmp_explorer_workspace_bytes)");
   GMP_CUDA(cudaMemcpyAsync(ws.node_ptr, meta.data(), (B + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   GMP_CUDA(cudaMemcpyAsync(ws.edge_ptr, meta.data() + (B + 1), (B + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
@@ -1160,6 +1253,7 @@ int run_forward(gmp_handle* h, int64_t B, const float* v, const int64_t* edge_in
   GMP_CUDA(cudaMemcpyAsync(ws.tile_ptr_e, tile_e, (B + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   GMP_CUDA(cudaMemcpyAsync(ws.tile_ptr_n, tile_n, (B + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   GMP_CUDA(cudaMemcpyAsync(ws.dense_off, dense_off.data(), (B + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  if (use_tc) GMP_CUDA(cudaMemcpyAsync(ws.tc_tab_off, tc_off.data(), (B + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
   // (pageable sources: cudaMemcpyAsync has staged them before returning, so the vectors may die)
 
   const size_t smem = Smem<E, true>::kBytes;     // node / obstacle kernels (two activation buffers)
@@ -1172,6 +1266,8 @@ int run_forward(gmp_handle* h, int64_t B, const float* v, const int64_t* edge_in
     GMP_CUDA(cudaFuncSetAttribute(node_loop_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     GMP_CUDA(cudaFuncSetAttribute(edge_msg_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MsgSmem<E>::kBytes));
     GMP_CUDA(cudaFuncSetAttribute(policy_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+    if constexpr (E == 32)
+      GMP_CUDA(cudaFuncSetAttribute(edge_feature_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<C>::kSmemBytes));
     attr_done = true;
   }
   const float* W = m.d_weights;
@@ -1217,7 +1313,25 @@ int run_forward(gmp_handle* h, int64_t B, const float* v, const int64_t* edge_in
   }
   tl.end(st);
   tl.begin(kPhEdgeFeature, st);
-  if (tile_e[B] > 0) {
+  bool tc_done = false;
+  if constexpr (E == 32) {
+    if (use_tc && tile_e[B] > 0) {
+      // tcgen05 path: re-tile the edge stream's obstacle tables into hi / lo TF32 planes, then one persistent CTA per SM
+      const int64_t tc_stride = tc_off[B];
+      if (use_obstacles && tc_stride > 0) {
+        tc_detail::obs_table_tc_kernel<<<dim3((unsigned)B, 3), 256, 0, st>>>(ws.tables, table_stride, ws.obs_ptr, ws.obs_tile_ptr,
+                                                                            ws.tc_tab_off, ws.tc_tables, tc_stride);
+        GMP_LAUNCH_CHECK();
+      }
+      static_assert(RowCfg<32>::R == 256, "a tensor-core unit is one 256-slot row tile");
+      edge_feature_tc_kernel<C><<<std::min<int>(tile_e[B], kNumSMs), 384, TcCfg<C>::kSmemBytes, st>>>(
+          W + m.w.tc_img, v, ws.csr_src, ws.csr_dst, ws.edge_ptr, ws.tile_ptr_e, (int)B, tile_e[B], ws.obs_ptr, ws.tc_tab_off,
+          ws.tc_tables, tc_stride, use_obstacles, ws.P, ws.Q);
+      GMP_LAUNCH_CHECK();
+      tc_done = true;
+    }
+  }
+  if (!tc_done && tile_e[B] > 0) {
     edge_feature_kernel<C, E><<<tile_e[B], kRtThreads, smem1, st>>>(m.w, W, v, ws.csr_src, ws.csr_dst, ws.edge_ptr, ws.tile_ptr_e,
                                                                   (int)B, ws.obs_ptr, ws.obs_tile_ptr, ws.tables, table_stride,
                                                                   use_obstacles, ws.P, ws.Q);
@@ -1302,6 +1416,14 @@ extern "C" int gmp_explorer_set_tensor(gmp_handle* h, const char* name, const fl
   return GMP_OK;
 }
 
+extern "C" int gmp_explorer_set_edge_feature_mode(gmp_handle* h, int mode) {
+  GMP_REQUIRE(h, "null handle");
+  GMP_REQUIRE(mode >= -1 && mode <= 1, "mode: -1 auto, 0 fp32 SIMT, 1 tcgen05 3xTF32");
+  GMP_REQUIRE(mode != 1 || h->ex.e == 0 || h->ex.e == 32, "the tensor-core edge-feature stage exists for embed_size 32 only");
+  h->ex.edge_feature_mode = mode;
+  return GMP_OK;
+}
+
 extern "C" int gmp_explorer_finalize(gmp_handle* h) {
   GMP_REQUIRE(h, "null handle");
   GMP_REQUIRE(h->ex.e != 0, "gmp_explorer_init first");
@@ -1315,9 +1437,11 @@ extern "C" int64_t gmp_explorer_workspace_bytes(const gmp_handle* h, int64_t n_g
   const int ot = (h->ex.e == 32) ? 32 : 16;
   // every graph may add one partially filled obstacle tile
   const int64_t obs_tiles = n_obs_total / ot + n_graphs;
+  // tensor-core table rows: every chunk of <= 96 obstacles is padded to a multiple of 16 rows
+  const int64_t tc_rows = h->ex.e == 32 ? n_obs_total + 16 * (n_obs_total / 96 + n_graphs) : 0;
   Carver cv(nullptr);
   ExWs ws;
-  return carve_explorer(cv, ws, h->ex.e, n_graphs, n_nodes_total, n_edges_total, obs_tiles) + 256;
+  return carve_explorer(cv, ws, h->ex.e, n_graphs, n_nodes_total, n_edges_total, obs_tiles, tc_rows) + 256;
 }
 
 #define GMP_DISPATCH(CC, EE, SS)                                                                                              \

@@ -39,11 +39,13 @@ struct ExplorerW {
   int p0_ef, p0_G, p0_H;             // policy.0: [Wct | b] ; (Wa+Wb)^T ; (-Wb)^T
   int p2;                            // policy.2: [Wt | b | policy.4 weight [E]]
   int goal_enc;                      // [E]
+  int tc_img;                        // tensor-core image of the edge-feature stage (explorer_tc.cuh), -1 if none
 };
 
 struct ExplorerModel {
   int c = 0, e = 0, s = 0;
   bool ready = false;
+  int edge_feature_mode = -1;        // -1 auto (tensor cores when e == 32), 0 fp32 SIMT, 1 tcgen05 3xTF32
   std::map<std::string, std::vector<float>> tensors;  // reference state_dict (live entries)
   ExplorerW w{};
   float* d_weights = nullptr;

@@ -190,6 +190,13 @@ class EncoderProcessDecoder:
 
     PHASES = ("csr_build", "goal_index", "obstacle_stream", "node_pre", "edge_feature", "node_loop", "edge_msg", "policy")
 
+    def set_edge_feature_mode(self, mode):
+        """Arithmetic of the edge-feature stage: "auto" (tcgen05 3xTF32 tensor cores when embed_size == 32),
+        "simt" (fp32 FMA) or "tc".  Both meet the 1e-4 logit tolerance; exists for A/B parity tests and profiling."""
+        self._ensure_uploaded()
+        code = {"auto": -1, "simt": 0, "tc": 1}[mode]
+        _lib.check(_lib.load().gmp_explorer_set_edge_feature_mode(self._handle, code))
+
     def set_timing(self, enable=True):
         """Record CUDA events around every phase of subsequent forwards (see ``last_timings``)."""
         self._ensure_uploaded()

@@ -59,6 +59,11 @@ int gmp_explorer_set_tensor(gmp_handle* h, const char* name, const float* data_h
 /* Validates that every live tensor arrived with the right size, builds the device-side packed
  * (transposed / algebraically pre-combined) weight image. */
 int gmp_explorer_finalize(gmp_handle* h);
+/* Arithmetic of the edge-feature stage (edge encoders + edge Blocks, model.py:120,123,130):
+ *   -1 auto (default): tcgen05 tensor cores with 3xTF32 split operands when embed_size == 32, fp32 FMA otherwise;
+ *    0 fp32 FMA (SIMT) always;  1 tensor cores (embed_size 32 only).
+ * Both meet the 1e-4 logit tolerance; the switch exists for A/B parity tests and profiling. */
+int gmp_explorer_set_edge_feature_mode(gmp_handle* h, int mode);
 
 /* Bytes of scratch gmp_explorer_forward needs for a batch of these totals. */
 int64_t gmp_explorer_workspace_bytes(const gmp_handle* h, int64_t n_graphs, int64_t n_nodes_total,

@@ -113,3 +113,48 @@ def test_errors(cuda_device):
     out = m(goal=v[0], loop=2, v=v[:1], obstacles=torch.zeros(0, 2, device=cuda_device),
             edge_index=torch.zeros(2, 0, dtype=torch.int64, device=cuda_device))
     assert out.shape == (1, 1) and float(out.abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize("tag,wfile,dims", [CASES[0], CASES[2]])
+def test_tensor_core_edge_stage_vs_simt_and_oracle(cuda_device, tag, wfile, dims):
+    """embed 32: the tcgen05 3xTF32 edge-feature stage (default) against the fp32 SIMT stage and the oracle, on a ragged
+    batch whose obstacle counts cover 0, one partial chunk, exactly 96, two chunks (97, 130) and three chunks (200)."""
+    from oracle import explorer as o_explorer
+    from oracle import knn_graph as o_knn
+    sd = torch.load(os.path.join(G, "weights", wfile), map_location="cpu")
+    m = make_model(wfile, dims, cuda_device)
+    c, s = dims[1], dims[3]
+    rng = np.random.default_rng(7)
+    graphs = []
+    for n, k, o in [(300, 12, 96), (40, 5, 0), (513, 9, 97), (129, 20, 5), (260, 8, 130), (64, 6, 200), (700, 10, 57)]:
+        v = rng.uniform(-1, 1, (n, c)).astype(np.float32)
+        ei = o_knn.knn_graph_edges(v, n, k)
+        obs = rng.uniform(-0.5, 0.5, (o, s)).astype(np.float32)
+        graphs.append((v, ei, v[1].copy(), obs))
+    node_ptr = np.cumsum([0] + [len(g[0]) for g in graphs])
+    edge_ptr = np.cumsum([0] + [g[1].shape[1] for g in graphs])
+    obs_ptr = np.cumsum([0] + [len(g[3]) for g in graphs])
+    V = torch.from_numpy(np.concatenate([g[0] for g in graphs])).to(cuda_device)
+    EI = torch.from_numpy(np.concatenate([g[1] for g in graphs], 1)).to(cuda_device)
+    GOAL = torch.from_numpy(np.stack([g[2] for g in graphs])).to(cuda_device)
+    OBS = torch.from_numpy(np.concatenate([g[3] for g in graphs])).to(cuda_device)
+    out = {}
+    for mode in ("tc", "simt"):
+        m.set_edge_feature_mode(mode)
+        out[mode] = m.forward_batch(V, EI, GOAL, OBS, node_ptr, edge_ptr, obs_ptr, loop=5).cpu().numpy()
+    m.use_obstacles = False
+    m.set_edge_feature_mode("tc")
+    noobs_tc = m.forward_batch(V, EI, GOAL, OBS, node_ptr, edge_ptr, obs_ptr, loop=5).cpu().numpy()
+    m.set_edge_feature_mode("simt")
+    noobs_simt = m.forward_batch(V, EI, GOAL, OBS, node_ptr, edge_ptr, obs_ptr, loop=5).cpu().numpy()
+    assert np.abs(noobs_tc - noobs_simt).max() < TOL
+    worst = 0.0
+    for g, (v, ei, goal, obs) in enumerate(graphs):
+        want = o_explorer.explorer_forward(sd, torch.from_numpy(v), torch.from_numpy(ei), torch.from_numpy(goal),
+                                           torch.from_numpy(obs), loop=5, dense=False, dtype=torch.float64).numpy()
+        for mode in ("tc", "simt"):
+            err = np.abs(out[mode][edge_ptr[g]:edge_ptr[g + 1]] - want).max()
+            worst = max(worst, err)
+            assert err < TOL, (tag, g, mode, err)
+    print("tc vs simt max |diff| %.3g; worst |err| vs fp64 oracle %.3g" % (np.abs(out["tc"] - out["simt"]).max(), worst))
+    assert np.abs(out["tc"] - out["simt"]).max() < TOL

@@ -1,0 +1,282 @@
+// Microbenchmark / bring-up test of the tcgen05 primitives in csrc/umma.cuh (B200 only):
+//   1. D = A.B^T with A in shared memory (SS) and in TMEM (TS), 1xTF32 and 3xTF32, error against fp64;
+//      tells whether operand conversion truncates and how close 3xTF32 gets to fp32;
+//   2. cycle counts: MMA group issue -> commit latency, tcgen05.ld / tcgen05.st throughput with 4 and 8 warps.
+// Build + run on the GPU box:
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I gnn_motion_planning_b200/csrc \
+//        -o tools/microbench/umma_tf32 tools/microbench/umma_tf32.cu && tools/microbench/umma_tf32
+#include <cuda_runtime.h>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "umma.cuh"
+
+namespace gmp {
+void set_error(const std::string&) {}
+int cuda_fail(cudaError_t, const char*, const char*, int) { return -1; }
+}  // namespace gmp
+using namespace gmp;
+
+constexpr int M = 128;
+
+// mode bit0: 3xTF32 (else 1x, raw fp32 bits fed to the tensor core); bit1: A from TMEM
+template <int N, int K>
+__global__ void __launch_bounds__(128) gemm_test(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D,
+                                                 int mode, long long* cycles) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  float* Ah = reinterpret_cast<float*>(smem);            // [K/4][128][4]
+  float* Al = Ah + M * K;
+  float* Bh = Al + M * K;                                // [K/4][N][4]
+  float* Bl = Bh + N * K;
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int t = threadIdx.x, warp = t >> 5;
+  const bool x3 = mode & 1, ts = mode & 2;
+  if (warp == 0) umma::tmem_alloc(&tmem_slot, 256);
+  if (t == 0) mbar_init(&bar, 1);
+  // operands -> shared memory
+  for (int i = t; i < M * K; i += 128) {
+    const int r = i / K, k = i % K;
+    const float x = A[i];
+    const float h = x3 ? umma::tf32_hi(x) : x;
+    Ah[((k / 4) * M + r) * 4 + (k % 4)] = h;
+    Al[((k / 4) * M + r) * 4 + (k % 4)] = x - h;
+  }
+  for (int i = t; i < N * K; i += 128) {
+    const int n = i / K, k = i % K;
+    const float x = B[i];
+    const float h = x3 ? umma::tf32_hi(x) : x;
+    Bh[((k / 4) * N + n) * 4 + (k % 4)] = h;
+    Bl[((k / 4) * N + n) * 4 + (k % 4)] = x - h;
+  }
+  umma::fence_proxy_async();
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tm = tmem_slot;
+  const uint32_t lane_base = tm + ((uint32_t)(warp * 32) << 16);
+  const uint32_t colD = 0, colAh = 64, colAl = 64 + K;   // K <= 64, N <= 64
+  if (ts) {
+    float row[K];
+    for (int k = 0; k < K; ++k) row[k] = A[t * K + k];
+    if (x3) {
+      umma::st_split<K>(lane_base + colAh, lane_base + colAl, row);
+    } else {
+      for (int c = 0; c < K; c += 8) umma::st8(lane_base + colAh + c, row + c);
+    }
+    umma::wait_st();
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  long long t0 = clock64();
+  if (t == 0) {
+    umma::fence_after_sync();
+    const uint32_t id = umma::idesc_tf32(M, N);
+    if (ts) {
+      if (x3) {
+        umma::gemm3_ts(tm + colD, tm + colAh, tm + colAl, smem_u32(Bh), smem_u32(Bl), N, 0, N, K, false);
+      } else {
+        for (int ks = 0; ks < K / 8; ++ks) umma::mma_ts(tm + colD, tm + colAh + ks * 8, umma::kmajor_desc(smem_u32(Bh), N, ks), id, ks > 0);
+      }
+    } else {
+      for (int ks = 0; ks < K / 8; ++ks) {
+        const uint64_t ah = umma::kmajor_desc(smem_u32(Ah), M, ks), al = umma::kmajor_desc(smem_u32(Al), M, ks);
+        const uint64_t bh = umma::kmajor_desc(smem_u32(Bh), N, ks), bl = umma::kmajor_desc(smem_u32(Bl), N, ks);
+        if (x3) {
+          umma::mma_ss(tm + colD, al, bh, id, ks > 0);
+          umma::mma_ss(tm + colD, ah, bl, id, 1);
+          umma::mma_ss(tm + colD, ah, bh, id, 1);
+        } else {
+          umma::mma_ss(tm + colD, ah, bh, id, ks > 0);
+        }
+      }
+    }
+    umma::commit(&bar);
+  }
+  __syncwarp();
+  mbar_wait(&bar, 0);
+  long long t1 = clock64();
+  umma::fence_after_sync();
+  float out[N];
+  for (int c = 0; c < N; c += 8) umma::ld8(lane_base + colD + c, out + c);
+  umma::wait_ld();
+  for (int n = 0; n < N; ++n) D[t * N + n] = out[n];
+  if (t == 0 && cycles) *cycles = t1 - t0;
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tm, 256);
+}
+
+// TMEM load / store throughput: every warp moves `iters` x 32 columns of its lane quarter
+__global__ void __launch_bounds__(256) tmem_bw(int iters, long long* out, float* sink) {
+  __shared__ uint32_t tmem_slot;
+  const int t = threadIdx.x, warp = t >> 5;
+  if (warp == 0) umma::tmem_alloc(&tmem_slot, 512);
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t base = tmem_slot + ((uint32_t)((warp & 3) * 32) << 16) + (warp >> 2) * 256;
+  float r[32];
+  for (int i = 0; i < 32; ++i) r[i] = (float)(t + i);
+  umma::st32(base, r);
+  umma::wait_st();
+  __syncthreads();
+  long long t0 = clock64();
+  float acc = 0.f;
+  for (int it = 0; it < iters; ++it) {
+    umma::ld32(base + (it & 7) * 32, r);
+    umma::wait_ld();
+    acc += r[it & 31];
+  }
+  __syncthreads();
+  long long t1 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    r[it & 31] += 1.0f;
+    umma::st32(base + (it & 7) * 32, r);
+  }
+  umma::wait_st();
+  __syncthreads();
+  long long t2 = clock64();
+  if (t == 0) { out[0] = t1 - t0; out[1] = t2 - t1; }
+  sink[t] = acc + r[0];
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem_slot, 512);
+}
+
+static float tf32_trunc(float x) { uint32_t u; memcpy(&u, &x, 4); u &= 0xFFFFE000u; memcpy(&x, &u, 4); return x; }
+static float tf32_rn(float x) { uint32_t u; memcpy(&u, &x, 4); u += 0x1000u; u &= 0xFFFFE000u; memcpy(&x, &u, 4); return x; }
+
+template <int N, int K>
+void run_case(const char* name) {
+  std::vector<float> A(M * K), B(N * K), D(M * N);
+  srand(1);
+  for (auto& x : A) x = (float)rand() / RAND_MAX * 2.f - 1.f;
+  for (auto& x : B) x = (float)rand() / RAND_MAX * 2.f - 1.f;
+  float *dA, *dB, *dD; long long* dc;
+  cudaMalloc(&dA, A.size() * 4); cudaMalloc(&dB, B.size() * 4); cudaMalloc(&dD, D.size() * 4); cudaMalloc(&dc, 8);
+  cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice);
+  const size_t smem = (size_t)(2 * M * K + 2 * N * K) * 4;
+  cudaFuncSetAttribute(gemm_test<N, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  for (int mode = 0; mode < 4; ++mode) {
+    cudaMemset(dD, 0, D.size() * 4);
+    long long cyc = 0;
+    for (int rep = 0; rep < 2; ++rep) gemm_test<N, K><<<1, 128, smem>>>(dA, dB, dD, mode, dc);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("%s mode %d: CUDA error %s\n", name, mode, cudaGetErrorString(e)); exit(1); }
+    cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost);
+    cudaMemcpy(&cyc, dc, 8, cudaMemcpyDeviceToHost);
+    double e64 = 0, e32 = 0, etr = 0, ern = 0;
+    for (int m = 0; m < M; ++m)
+      for (int n = 0; n < N; ++n) {
+        double ref = 0, rtr = 0, rrn = 0; float f32 = 0.f;
+        for (int k = 0; k < K; ++k) {
+          ref += (double)A[m * K + k] * (double)B[n * K + k];
+          f32 = fmaf(A[m * K + k], B[n * K + k], f32);
+          rtr += (double)tf32_trunc(A[m * K + k]) * (double)tf32_trunc(B[n * K + k]);
+          rrn += (double)tf32_rn(A[m * K + k]) * (double)tf32_rn(B[n * K + k]);
+        }
+        const double d = D[m * N + n];
+        e64 = fmax(e64, fabs(d - ref)); e32 = fmax(e32, fabs((double)f32 - ref));
+        etr = fmax(etr, fabs(d - rtr)); ern = fmax(ern, fabs(d - rrn));
+      }
+    printf("%s N=%d K=%d %s %s: max|D-fp64|=%.3e (fp32 fma chain: %.3e)  |D-trunc model|=%.3e |D-rn model|=%.3e  issue->commit %lld cyc\n",
+           name, N, K, (mode & 2) ? "A=TMEM" : "A=SMEM", (mode & 1) ? "3xTF32" : "1xTF32", e64, e32, etr, ern, cyc);
+  }
+  cudaFree(dA); cudaFree(dB); cudaFree(dD); cudaFree(dc);
+}
+
+int main2();
+int main() {
+  main2();
+  return 0;
+  run_case<32, 32>("gemm");
+  run_case<64, 32>("gemm");
+  run_case<32, 64>("gemm");
+  run_case<64, 64>("gemm");
+  long long* dout; float* sink; long long h[2];
+  cudaMalloc(&dout, 16); cudaMalloc(&sink, 256 * 4);
+  for (int threads : {128, 256}) {
+    const int iters = 4096;
+    tmem_bw<<<1, threads>>>(iters, dout, sink);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("tmem_bw: CUDA error %s\n", cudaGetErrorString(e)); return 1; }
+    cudaMemcpy(h, dout, 16, cudaMemcpyDeviceToHost);
+    const double bytes = (double)iters * threads * 32 * 4;
+    printf("tmem %d threads: ld32+wait %.1f cyc/iter (%.1f B/cyc/SM), st32 %.1f cyc/iter (%.1f B/cyc/SM)\n", threads, (double)h[0] / iters,
+           bytes / h[0], (double)h[1] / iters, bytes / h[1]);
+  }
+  return 0;
+}
+
+// ---- part 3: MMA issue patterns.  `n_mma` TS-mode MMAs (M=128, K=8 each) round-robin over `n_acc` accumulators,
+// issued by `n_issuers` threads (one per warpgroup-of-4 warps) each with its own accumulators + barrier.
+template <int N>
+__global__ void __launch_bounds__(256) mma_pattern(int n_mma, int n_acc, int n_issuers, long long* out) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  float* Bh = reinterpret_cast<float*>(smem);   // [2][N][4] one k-step of B, zeros
+  __shared__ uint64_t bar[2];
+  __shared__ uint32_t tmem_slot;
+  const int t = threadIdx.x, warp = t >> 5;
+  for (int i = t; i < 2 * N * 4; i += blockDim.x) Bh[i] = 0.f;
+  if (warp == 0) umma::tmem_alloc(&tmem_slot, 512);
+  if (t == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
+  umma::fence_proxy_async();
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tm = tmem_slot;
+  const int grp = t >> 7;
+  long long t0 = clock64();
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);          // provably warp-uniform
+  if ((warp_u & 3) == 0 && (warp_u >> 2) < n_issuers) {
+    const uint32_t tm_u = __shfl_sync(0xffffffffu, tm, 0);
+    const int grp_u = warp_u >> 2;
+    if (umma::elect_one()) {
+      const uint32_t id = umma::idesc_tf32(128, N);
+      const uint64_t bd = umma::kmajor_desc(smem_u32(Bh), N, 0);
+      const uint32_t d0 = tm_u + grp_u * 256, a0 = tm_u + grp_u * 256 + 192;
+      const uint32_t amask = (uint32_t)(n_acc - 1);   // n_acc is a power of two
+#pragma unroll 8
+      for (int i = 0; i < n_mma; ++i) umma::mma_ts(d0 + (i & amask) * N, a0 + (i & 7) * 8, bd, id, 1u);
+      umma::commit(&bar[grp_u]);
+    }
+    __syncwarp();
+  }
+  if (grp < n_issuers) mbar_wait(&bar[grp], 0);
+  long long t1 = clock64();
+  __syncthreads();
+  if (t == 0) out[0] = t1 - t0;
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tm, 512);
+}
+
+template <int N>
+void run_pattern(long long* dout) {
+  const size_t smem = 2 * N * 16;
+  for (int n_mma : {6, 12, 24, 48, 96, 192})
+    for (int issuers : {1, 2}) {
+      const int n_acc = (N <= 64 && n_mma == 96) ? 2 : 1;
+      long long h = 0;
+      for (int rep = 0; rep < 2; ++rep) mma_pattern<N><<<1, 256, smem>>>(n_mma, n_acc, issuers, dout);
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) { printf("mma_pattern: CUDA error %s\n", cudaGetErrorString(e)); exit(1); }
+      cudaMemcpy(&h, dout, 8, cudaMemcpyDeviceToHost);
+      printf("mma N=%3d: %3d MMAs/issuer, %d issuer(s), %d accumulator(s): %lld cyc total, %.1f cyc/MMA/issuer\n", N, n_mma, issuers, n_acc, h,
+             (double)h / n_mma);
+    }
+}
+
+int main2() {
+  long long* dout;
+  cudaMalloc(&dout, 16);
+  run_pattern<32>(dout);
+  run_pattern<64>(dout);
+  run_pattern<128>(dout);
+  return 0;
+}

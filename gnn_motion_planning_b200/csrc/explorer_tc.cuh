@@ -332,23 +332,36 @@ __global__ void __launch_bounds__(384, 1) edge_feature_tc_kernel(
           for (int j = 0; j < Cf::kOcMax; j += 16)
             if (j < per) umma::ld16(tc + Cf::cSC + j, sc + j);
           umma::wait_ld();
-          float mnew = m;
-#pragma unroll
-          for (int o = 0; o < Cf::kOcMax; ++o)
-            if (o < cnt) mnew = fmaxf(mnew, sc[o]);
-          const float corr = exp2f(m - mnew);
-          float lsum = l * corr;
-#pragma unroll
-          for (int o = 0; o < Cf::kOcMax; ++o) {
-            const float p = (o < cnt) ? exp2f(sc[o] - mnew) : 0.0f;
-            lsum += p;
-            sc[o] = p;
-          }
-          l = lsum;
-          m = mnew;
+          // padded table rows score 0: mask them to -inf (weight 0); only the 16-column pieces at / after `cnt`
 #pragma unroll
           for (int j = 0; j < Cf::kOcMax; j += 16)
-            if (j < per) umma::st_split<16>(tc + Cf::cSC + j, tc + Cf::cPL + j, sc + j);
+            if (j < per && j + 16 > cnt) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (j + i >= cnt) sc[j + i] = -INFINITY;
+            }
+          float mnew = m;
+#pragma unroll
+          for (int j = 0; j < Cf::kOcMax; j += 16)
+            if (j < per) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) mnew = fmaxf(mnew, sc[j + i]);
+            }
+          const float corr = umma::ex2_approx(m - mnew);
+          float lsum = l * corr;
+#pragma unroll
+          for (int j = 0; j < Cf::kOcMax; j += 16)
+            if (j < per) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float p = umma::ex2_approx(sc[j + i] - mnew);
+                lsum += p;
+                sc[j + i] = p;
+              }
+              umma::st_split<16>(tc + Cf::cSC + j, tc + Cf::cPL + j, sc + j);
+            }
+          l = lsum;
+          m = mnew;
           publish();
           await();   // P.V of this chunk
           float pv[E];

@@ -135,8 +135,11 @@ __device__ __forceinline__ float tf32_rna(float x) {
 }
 __device__ __forceinline__ float tf32_hi(float x) { return tf32_rna(x); }
 
-// store N values (N % 8 == 0) of this thread's row as hi / lo planes at TMEM columns hi_addr / lo_addr
-template <int N>
+// store N values (N % 8 == 0) of this thread's row as hi / lo planes at TMEM columns hi_addr / lo_addr.
+// hi is rounded to nearest; lo = x - hi is exact in fp32 and is stored as is: the tensor core drops its 13 low
+// mantissa bits on read (measured: operand conversion truncates, tools/microbench/umma_tf32.cu), an error of at most
+// 2^-10 |lo| <= 2^-22 |x| -- 3 instructions per element instead of 5 with an explicitly rounded lo (ROUND_LO).
+template <int N, bool ROUND_LO = false>
 __device__ __forceinline__ void st_split(uint32_t hi_addr, uint32_t lo_addr, const float* x) {
 #pragma unroll
   for (int c = 0; c < N; c += 8) {
@@ -144,11 +147,18 @@ __device__ __forceinline__ void st_split(uint32_t hi_addr, uint32_t lo_addr, con
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       h[i] = tf32_rna(x[c + i]);
-      l[i] = tf32_rna(x[c + i] - h[i]);
+      l[i] = ROUND_LO ? tf32_rna(x[c + i] - h[i]) : x[c + i] - h[i];
     }
     st8(hi_addr + c, h);
     st8(lo_addr + c, l);
   }
+}
+
+// 2^x for x <= 0 (softmax weights): one MUFU.EX2; results below 2^-126 flush to zero
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -159,7 +169,7 @@ __device__ __forceinline__ void mbar_wait_guard(uint64_t* bar, uint32_t phase) {
   const uint32_t addr = smem_u32(bar);
   uint32_t done = 0, spins = 0;
   while (true) {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x4000;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                  : "=r"(done)
                  : "r"(addr), "r"(phase)
                  : "memory");

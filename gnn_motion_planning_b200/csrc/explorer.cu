@@ -30,6 +30,7 @@
 //
 // All dense math is fp32 FMA through the row-tile machinery of rowtile.cuh (see there for the layout).
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "handle.h"
@@ -1104,12 +1105,20 @@ int explorer_build_image(ExplorerModel& m) {
   // ---- tensor-core image of the edge-feature stage (e = 32): hi / lo TF32 planes in the order of TcCfg<C>
   w.tc_img = -1;
   if (e == 32) {
-    const int k0 = (2 * c + 7) / 8 * 8;
+    const int k0 = (2 * c + 7) / 8 * 8, k4 = (2 * c + 3) / 4 * 4;
     w.tc_img = pk.begin();
-    put_planes(pk, window(T("edge_free_code.0.weight"), 2 * c, 0, e, 0, 2 * c), e, 2 * c, k0);
+    {
+      // first encoder layers stacked: rows 0..e-1 edge_free_code.0, rows e..2e-1 edge_code.0 (planes + plain fp32 copy)
+      std::vector<double> enc0 = window(T("edge_free_code.0.weight"), 2 * c, 0, e, 0, 2 * c);
+      const std::vector<double> ec0 = window(T("edge_code.0.weight"), 2 * c, 0, e, 0, 2 * c);
+      enc0.insert(enc0.end(), ec0.begin(), ec0.end());
+      put_planes(pk, enc0, 2 * e, 2 * c, k0);
+      std::vector<float> plain((size_t)2 * e * k4, 0.f);
+      for (int n = 0; n < 2 * e; ++n)
+        for (int k = 0; k < 2 * c; ++k) plain[(size_t)n * k4 + k] = (float)enc0[(size_t)n * 2 * c + k];
+      pk.put(plain);
+    }
     put_planes(pk, window(T("edge_free_code.2.weight"), e, 0, e, 0, e), e, e, e);
-    put_planes(pk, window(T("edge_code.0.weight"), 2 * c, 0, e, 0, 2 * c), e, 2 * c, k0);
-    put_planes(pk, window(T("edge_code.2.weight"), e, 0, e, 0, e), e, e, e);
     for (int i = 0; i < 3; ++i) {
       const std::string p = "edge_attentions." + std::to_string(i) + ".";
       const auto& Wq = T(p + "attention.query.weight");
@@ -1127,16 +1136,33 @@ int explorer_build_image(ExplorerModel& m) {
       put_planes(pk, window(T(p + "map_feed.w_1.weight"), e, 0, e, 0, e), e, e, e);
       put_planes(pk, window(T(p + "map_feed.w_2.weight"), e, 0, e, 0, e), e, e, e);
     }
+    std::vector<double> pb(e);
     {
       const auto& Wp = T("policy.0.weight");
       const auto& W0 = T("process.lin_0.0.weight");
       std::vector<double> QP = window(Wp, 3 * e, 0, e, 2 * e, e), Pef = window(W0, 5 * e, 0, e, 3 * e, e);
       QP.insert(QP.end(), Pef.begin(), Pef.end());
       put_planes(pk, QP, 2 * e, e, e);
-      put_planes(pk, window(W0, 5 * e, 0, e, 4 * e, e), e, e, e);
+      // edge_code = W_ec2 relu(.) + b_ec2 is only ever consumed through lin_0's edge_code columns W5 (model.py:39,120):
+      // fold  W5 edge_code = (W5 W_ec2) relu(.) + W5 b_ec2  so that edge_code is never materialised
+      const std::vector<double> W5 = window(W0, 5 * e, 0, e, 4 * e, e);
+      const auto& Wec2 = T("edge_code.2.weight");
+      const auto& bec2 = T("edge_code.2.bias");
+      const auto& b0 = T("process.lin_0.0.bias");
+      std::vector<double> W52((size_t)e * e);
+      for (int n = 0; n < e; ++n) {
+        double bsum = b0[n];
+        for (int j = 0; j < e; ++j) bsum += W5[(size_t)n * e + j] * (double)bec2[j];
+        pb[n] = bsum;
+        for (int k = 0; k < e; ++k) {
+          double sum = 0;
+          for (int j = 0; j < e; ++j) sum += W5[(size_t)n * e + j] * (double)Wec2[(size_t)j * e + k];
+          W52[(size_t)n * e + k] = sum;
+        }
+      }
+      put_planes(pk, W52, e, e, e);
     }
-    pk.put(T("edge_free_code.0.bias")); pk.put(T("edge_free_code.2.bias"));
-    pk.put(T("edge_code.0.bias")); pk.put(T("edge_code.2.bias"));
+    pk.put(T("edge_free_code.0.bias")); pk.put(T("edge_code.0.bias")); pk.put(T("edge_free_code.2.bias"));
     for (int i = 0; i < 3; ++i) {
       const std::string p = "edge_attentions." + std::to_string(i) + ".";
       pk.put(T(p + "attention.layer_norm.weight")); pk.put(T(p + "attention.layer_norm.bias"));
@@ -1144,7 +1170,7 @@ int explorer_build_image(ExplorerModel& m) {
       pk.put(T(p + "map_feed.layer_norm.weight")); pk.put(T(p + "map_feed.layer_norm.bias"));
     }
     pk.put(T("policy.0.bias"));
-    pk.put(T("process.lin_0.0.bias"));
+    pk.put(pb);
   }
   pk.begin();
   for (int q = 0; q < 4 * e + 64; ++q) pk.buf.push_back(0.f);  // slack: stages may over-read up to a few vectors
@@ -1169,6 +1195,7 @@ struct ExWs {
   float *tables, *X0, *D0, *H, *Xg, *AGG, *A, *B, *P, *Q;
   int64_t* tc_tab_off;   // tensor-core edge-feature stage: per-graph float offset of its obstacle-table units
   float* tc_tables;      // 3 blocks x tc_rows x 128 floats (hi / lo planes of M and V per 96-obstacle chunk)
+  int4* tc_unit_meta;    // per 256-slot unit: first slot, graph's end slot, obstacle count, table offset
 };
 
 int64_t carve_explorer(Carver& cv, ExWs& ws, int e, int64_t B, int64_t Nt, int64_t Et, int64_t obs_tiles, int64_t tc_rows) {
@@ -1199,7 +1226,18 @@ int64_t carve_explorer(Carver& cv, ExWs& ws, int e, int64_t B, int64_t Nt, int64
   ws.Q = cv.take<float>(Et * e);
   ws.tc_tab_off = cv.take<int64_t>(B + 1);
   ws.tc_tables = cv.take<float>(3 * tc_rows * 4 * e);
+  ws.tc_unit_meta = cv.take<int4>(e == 32 ? Et / 256 + B + 1 : 0);
   return cv.bytes();
+}
+
+// head start (SM cycles) of tile 0 over tile 1 in the tensor-core edge-feature kernel; GMP_TC_PHASE_DELAY overrides (tuning)
+int tc_phase_delay() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = std::getenv("GMP_TC_PHASE_DELAY");
+    v = e ? std::atoi(e) : 0;
+  }
+  return v;
 }
 
 template <int C, int E, int S>
@@ -1242,6 +1280,7 @@ int run_forward(gmp_handle* h, int64_t B, const float* v, const int64_t* edge_in
       tc_off[g + 1] = tc_off[g] + (int64_t)nch * tc_per(no, nch) * 4 * E;
     }
   const int64_t tc_rows = tc_off[B] / (4 * E);
+  GMP_REQUIRE(tc_off[B] < (int64_t)1 << 31, "too many obstacle rows in one call for the tensor-core table index");
   Carver cv(workspace);
   ExWs ws;
   const int64_t need = carve_explorer(cv, ws, E, B, Nt, Et, obs_tiles, tc_rows);
@@ -1324,9 +1363,12 @@ int run_forward(gmp_handle* h, int64_t B, const float* v, const int64_t* edge_in
         GMP_LAUNCH_CHECK();
       }
       static_assert(RowCfg<32>::R == 256, "a tensor-core unit is one 256-slot row tile");
+      tc_detail::unit_meta_kernel<<<(tile_e[B] + 255) / 256, 256, 0, st>>>(ws.tile_ptr_e, (int)B, tile_e[B], ws.edge_ptr, ws.obs_ptr,
+                                                                          ws.tc_tab_off, ws.tc_unit_meta);
+      GMP_LAUNCH_CHECK();
       edge_feature_tc_kernel<C><<<std::min<int>(tile_e[B], kNumSMs), 384, TcCfg<C>::kSmemBytes, st>>>(
-          W + m.w.tc_img, v, ws.csr_src, ws.csr_dst, ws.edge_ptr, ws.tile_ptr_e, (int)B, tile_e[B], ws.obs_ptr, ws.tc_tab_off,
-          ws.tc_tables, tc_stride, use_obstacles, ws.P, ws.Q);
+          W + m.w.tc_img, v, ws.csr_src, ws.csr_dst, ws.tc_unit_meta, tile_e[B], ws.tc_tables, tc_stride, use_obstacles, tc_phase_delay(),
+          ws.P, ws.Q);
       GMP_LAUNCH_CHECK();
       tc_done = true;
     }
@@ -1437,8 +1479,8 @@ extern "C" int64_t gmp_explorer_workspace_bytes(const gmp_handle* h, int64_t n_g
   const int ot = (h->ex.e == 32) ? 32 : 16;
   // every graph may add one partially filled obstacle tile
   const int64_t obs_tiles = n_obs_total / ot + n_graphs;
-  // tensor-core table rows: every chunk of <= 96 obstacles is padded to a multiple of 16 rows
-  const int64_t tc_rows = h->ex.e == 32 ? n_obs_total + 16 * (n_obs_total / 96 + n_graphs) : 0;
+  // tensor-core table rows: every sub-chunk of <= 64 obstacles is padded to a multiple of 16 rows
+  const int64_t tc_rows = h->ex.e == 32 ? n_obs_total + 16 * (n_obs_total / 48 + n_graphs) : 0;
   Carver cv(nullptr);
   ExWs ws;
   return carve_explorer(cv, ws, h->ex.e, n_graphs, n_nodes_total, n_edges_total, obs_tiles, tc_rows) + 256;

@@ -20,43 +20,54 @@
 //
 // TMEM columns of a tile (256 of the CTA's 512): XH [0,32) XL [32,64) A operand; A1 [64,128) accumulators
 // (Gx | Vx, FFN, Q | P); SC [128,224) scores -> probabilities hi (in place); PL [0,96) probabilities lo (overlays the
-// dead XH/XL/Gx); PV [224,256).
+// dead XH/XL/Gx); PV [224,256); in the tail HH [160,192) HL [192,224) hold the hidden layer of edge_code.
+//
+// Per-tile program (MMA round trips): [edge_free_code.0 if 2c > 8, else plain FMAs] -> edge_free_code.2 -> 3 x { Gx|Vx +
+// scores, P.V (per <=96-obstacle chunk), map_feed.w_1, map_feed.w_2 } -> [edge_code.0 if 2c > 8] -> { Q | P_ef, P += (W5
+// W_ec2) hidden_ec }: edge_code.2 is folded into lin_0's edge_code columns on the host, so edge_code itself never exists.
 #pragma once
+#include <type_traits>
 #include "handle.h"
 #include "rowtile.cuh"
 #include "umma.cuh"
 
 namespace gmp {
 
-// obstacle chunking shared by host and device: a graph's O obstacles are processed in nch chunks of `per` (multiple
-// of 16, <= 96) table rows, zero padded
-__host__ __device__ inline int tc_nchunks(int O) { return (O + 95) / 96; }
+// obstacle chunking shared by host and device: up to 96 obstacles are one sub-chunk; more are split into nch sub-chunks of
+// `per` (multiple of 16, <= 64) table rows, zero padded; two consecutive sub-chunks (<= 128 obstacles) form one table load
+// and share one scores stage
+__host__ __device__ inline int tc_nchunks(int O) { return O <= 96 ? (O > 0) : (O + 63) / 64; }
 __host__ __device__ inline int tc_per(int O, int nch) { return nch ? ((O + nch - 1) / nch + 15) / 16 * 16 : 0; }
 
 template <int C>
 struct TcCfg {
   static constexpr int E = 32;
   static constexpr int K0 = (2 * C + 7) / 8 * 8;        // encoder input width padded to the MMA K step
-  static constexpr int kOcMax = 96;
-  // float offsets in the TC weight image; every matrix is [hi plane | lo plane], a plane is float[K/4][N][4]
-  static constexpr int EF0 = 0;                          // edge_free_code.0   N=32 K=K0
-  static constexpr int EF2 = EF0 + 2 * E * K0;           // edge_free_code.2   N=32 K=32
-  static constexpr int EC0 = EF2 + 2 * E * E;            // edge_code.0
-  static constexpr int EC2 = EC0 + 2 * E * K0;           // edge_code.2
-  static constexpr int BLK = EC2 + 2 * E * E;            // + b*kBlk: GV (N=64: G rows | Wv rows) | W1 | W2
+  static constexpr int K4 = (2 * C + 3) / 4 * 4;        // ... padded to a float4 (SIMT first layer)
+  static constexpr bool kSimtIn = 2 * C <= 8;           // first encoder layers as plain FMAs (cheaper than an MMA round trip)
+  static constexpr int kOcMax = 96;                      // obstacle rows of a lone sub-chunk
+  static constexpr int kOcMax2 = 64;                     // ... of each sub-chunk of a pair
+  // float offsets in the TC weight image; an MMA matrix is [hi plane | lo plane], a plane is float[K/4][N][4]
+  static constexpr int ENC0 = 0;                         // N=64: edge_free_code.0 rows | edge_code.0 rows, K=K0
+  static constexpr int ENC0F = ENC0 + 2 * 64 * K0;       // the same as plain fp32 float[64][K4]
+  static constexpr int EF2 = ENC0F + 64 * K4;            // edge_free_code.2   N=32 K=32
+  static constexpr int BLK = EF2 + 2 * E * E;            // + b*kBlk: GV (N=64: G rows | Wv rows) | W1 | W2
   static constexpr int kBlk = 2 * 64 * E + 4 * E * E;
   static constexpr int oW1 = 2 * 64 * E, oW2 = oW1 + 2 * E * E;
   static constexpr int QP = BLK + 3 * kBlk;              // N=64: policy.0 edge_free cols (Q) | lin_0.0 edge_free cols (P)
-  static constexpr int W5 = QP + 2 * 64 * E;             // lin_0.0 edge_code cols
-  static constexpr int VEC = W5 + 2 * E * E;
+  static constexpr int W52 = QP + 2 * 64 * E;            // lin_0.0 edge_code cols . edge_code.2   (N=32 K=32)
+  static constexpr int VEC = W52 + 2 * E * E;
   // vectors (offsets from VEC)
-  static constexpr int vEF0b = 0, vEF2b = 32, vEC0b = 64, vEC2b = 96, vBLK = 128 /* +b*192: ln1g ln1b b1 b2 ln2g ln2b */,
+  static constexpr int vEF0b = 0, vEC0b = 32, vEF2b = 64, vBLK = 96 /* +b*192: ln1g ln1b b1 b2 ln2g ln2b */,
                        vQb = vBLK + 3 * 192, vPb = vQb + 32, kVec = vPb + 32;
   static constexpr int kImage = VEC + kVec;              // floats
-  static constexpr int kTab = 4 * E * kOcMax;            // floats: Mt hi | Mt lo | Vt hi | Vt lo
+  static constexpr int kTab = 2 * 4 * E * kOcMax2;       // floats: two sub-chunks of [Mt hi | Mt lo | Vt hi | Vt lo] (>= one of 96 rows)
   static constexpr size_t kSmemBytes = (size_t)(kImage + kTab) * sizeof(float);
   // TMEM columns of a tile
-  static constexpr int cXH = 0, cXL = 32, cA1 = 64, cSC = 128, cPL = 0, cPV = 224;
+  static constexpr int cXH = 0, cXL = 32, cA1 = 64, cSC = 128, cSC1 = 192, cPL = 0;
+  // P.V accumulator: lone sub-chunk -> cPV1 (PL may reach column 96); pair -> cPV2 (= dead Gx; SC1 occupies cPV1)
+  static constexpr int cPV1 = 224, cPV2 = cA1;
+  static constexpr int cHH = 160, cHL = 192;             // tail: hidden layer of edge_code (A operand of W52), also its inputs
 };
 
 namespace tc_detail {
@@ -98,6 +109,17 @@ __global__ void __launch_bounds__(256) obs_table_tc_kernel(const float* __restri
   }
 }
 
+// per 256-slot unit: (first CSR slot, end slot of its graph, obstacle count, float offset of the graph's table units)
+// -- one 16-byte load per unit in the main kernel instead of a binary search plus four dependent loads
+__global__ void __launch_bounds__(256) unit_meta_kernel(const int32_t* __restrict__ tile_ptr, int n_graphs, int n_units,
+                                                        const int32_t* __restrict__ edge_ptr, const int32_t* __restrict__ obs_ptr,
+                                                        const int64_t* __restrict__ tc_tab_off, int4* __restrict__ meta) {
+  const int u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= n_units) return;
+  const int g = find_segment(tile_ptr, n_graphs, u);
+  meta[u] = make_int4(edge_ptr[g] + (u - tile_ptr[g]) * 256, edge_ptr[g + 1], obs_ptr[g + 1] - obs_ptr[g], (int)tc_tab_off[g]);
+}
+
 template <int N>
 __device__ __forceinline__ void ld_cols(uint32_t taddr, float* dst) {
   static_assert(N % 16 == 0, "N % 16");
@@ -107,19 +129,22 @@ __device__ __forceinline__ void ld_cols(uint32_t taddr, float* dst) {
   }
 }
 
+// LayerNorm of one row held in registers (biased variance, torch.nn.LayerNorm); sums run as four independent chains so
+// that a lone warp on a scheduler is not serialised on the 4-cycle FADD latency
 template <int N>
 __device__ __forceinline__ void layernorm_row(float* x, const float* __restrict__ gamma, const float* __restrict__ beta, float eps) {
-  float mu = 0.f;
+  static_assert(N % 4 == 0, "N % 4");
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-  for (int n = 0; n < N; ++n) mu += x[n];
-  mu *= (1.0f / N);
-  float var = 0.f;
+  for (int n = 0; n < N; n += 4) { s0 += x[n]; s1 += x[n + 1]; s2 += x[n + 2]; s3 += x[n + 3]; }
+  const float mu = ((s0 + s1) + (s2 + s3)) * (1.0f / N);
+  float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
 #pragma unroll
-  for (int n = 0; n < N; ++n) {
-    const float d = x[n] - mu;
-    var = fmaf(d, d, var);
+  for (int n = 0; n < N; n += 4) {
+    const float d0 = x[n] - mu, d1 = x[n + 1] - mu, d2 = x[n + 2] - mu, d3 = x[n + 3] - mu;
+    v0 = fmaf(d0, d0, v0); v1 = fmaf(d1, d1, v1); v2 = fmaf(d2, d2, v2); v3 = fmaf(d3, d3, v3);
   }
-  var *= (1.0f / N);
+  const float var = ((v0 + v1) + (v2 + v3)) * (1.0f / N);
   const float rstd = 1.0f / sqrtf(var + eps);
 #pragma unroll
   for (int n = 0; n < N; ++n) x[n] = (x[n] - mu) * rstd * gamma[n] + beta[n];
@@ -130,9 +155,8 @@ __device__ __forceinline__ void layernorm_row(float* x, const float* __restrict_
 template <int C>
 __global__ void __launch_bounds__(384, 1) edge_feature_tc_kernel(
     const float* __restrict__ tcw, const float* __restrict__ v, const int32_t* __restrict__ csr_src,
-    const int32_t* __restrict__ csr_dst, const int32_t* __restrict__ edge_ptr, const int32_t* __restrict__ tile_ptr, int n_graphs,
-    int n_units, const int32_t* __restrict__ obs_ptr, const int64_t* __restrict__ tc_tab_off, const float* __restrict__ tc_tables,
-    int64_t tc_tab_stride, int use_obstacles, float* __restrict__ P, float* __restrict__ Q) {
+    const int32_t* __restrict__ csr_dst, const int4* __restrict__ unit_meta, int n_units, const float* __restrict__ tc_tables,
+    int64_t tc_tab_stride, int use_obstacles, int phase_delay, float* __restrict__ P, float* __restrict__ Q) {
   using Cf = TcCfg<C>;
   constexpr int E = 32, K0 = Cf::K0;
   extern __shared__ __align__(128) float smem_tc[];
@@ -162,10 +186,10 @@ __global__ void __launch_bounds__(384, 1) edge_feature_tc_kernel(
   const int n_blocks = use_obstacles ? 3 : 0;
 
   if (warp_u >= 8) {
-    // warpgroup 2 hands most of its registers to the two compute warpgroups (per SM sub-partition: 2 x 232 + 40 <= 512)
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    // warpgroup 2 hands most of its registers to the two compute warpgroups (per SM sub-partition: 2 x 224 + 56 <= 512)
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
   }
   if (warp_u > 8) {
     // warps 9-11 only pad the issuer's warpgroup
@@ -173,83 +197,166 @@ __global__ void __launch_bounds__(384, 1) edge_feature_tc_kernel(
     // =================================================================== MMA issuer / table loader
     const uint32_t tm_u = __shfl_sync(0xffffffffu, tm, 0);
     const uint32_t img_s = smem_u32(img), tab_s = smem_u32(tabbuf);
-    uint32_t rph[2] = {0, 0}, full_ph = 0, free_ph = 0;
-    // table cursor: next (unit, blk, chunk) to load
-    int cu_unit = blockIdx.x, cu_blk = 0, cu_c = 0;
+    uint32_t rph[2] = {0, 0}, full_ph = 0;
+    // unit metadata, one unit ahead of its use (uniform: every lane loads the same 16 bytes)
+    auto load_meta = [&](int u) {
+      int4 mm = make_int4(0, 0, 0, 0);
+      if (u < n_units) mm = __ldg(unit_meta + u);
+      mm.z = __shfl_sync(0xffffffffu, mm.z, 0);
+      mm.w = __shfl_sync(0xffffffffu, mm.w, 0);
+      return mm;
+    };
+    int4 meta_cur = load_meta(blockIdx.x), meta_next = load_meta(blockIdx.x + gridDim.x);
+    int cur_unit = blockIdx.x;
+    // table cursor: next (unit, blk, pair of sub-chunks) to load.  tab_busy: the buffer holds (or is receiving) a table
+    // whose P.V products have not all retired yet
+    int cu_unit = blockIdx.x, cu_blk = 0, cu_s = 0;
+    bool tab_busy = false;
     auto cursor_load = [&]() {   // loads the cursor's table (skipping graphs without obstacles) and advances; uniform
+      if (tab_busy) return;
       while (cu_unit < n_units) {
-        int g = find_segment(tile_ptr, n_graphs, cu_unit);
-        int O = obs_ptr[g + 1] - obs_ptr[g];
-        g = __shfl_sync(0xffffffffu, g, 0);
-        O = __shfl_sync(0xffffffffu, O, 0);
+        const int4 mm = cu_unit == cur_unit ? meta_cur : (cu_unit == cur_unit + (int)gridDim.x ? meta_next : load_meta(cu_unit));
+        const int O = mm.z;
         const int nch = tc_nchunks(O), per = tc_per(O, nch);
         if (n_blocks == 0 || nch == 0) { cu_unit += gridDim.x; continue; }
-        long long off = tc_tab_off[g];
-        off = __shfl_sync(0xffffffffu, off, 0);
-        const float* src = tc_tables + (size_t)cu_blk * tc_tab_stride + off + (size_t)cu_c * (4 * E * per);
-        const uint32_t bytes = (uint32_t)(4 * E * per) * 4u;
+        const int ns = min(2, nch - 2 * cu_s);
+        const float* src = tc_tables + (size_t)cu_blk * tc_tab_stride + (size_t)mm.w + (size_t)(2 * cu_s) * (4 * E * per);
+        const uint32_t bytes = (uint32_t)(ns * 4 * E * per) * 4u;
         if (umma::elect_one()) {
           mbar_expect_tx(&bar_tabfull, bytes);
           tma_bulk_g2s(tabbuf, src, bytes, &bar_tabfull);
         }
         __syncwarp();
-        if (++cu_c == nch) { cu_c = 0; if (++cu_blk == n_blocks) { cu_blk = 0; cu_unit += gridDim.x; } }
+        tab_busy = true;
+        if (2 * (++cu_s) >= nch) { cu_s = 0; if (++cu_blk == n_blocks) { cu_blk = 0; cu_unit += gridDim.x; } }
         return;
       }
     };
     cursor_load();
-    auto b_hi = [&](int off) { return img_s + (uint32_t)off * 4u; };
+#ifdef GMP_TC_PROFILE
+    long long prof_ready[2] = {0, 0}, prof_tab = 0, prof_free = 0, prof_t0 = clock64();
+    long long prof_issue[5] = {0, 0, 0, 0, 0};   // K0-wide encoder layer, 32x32, GV (+scores), P.V, Q|P
+#endif
+    // lo words of the weight descriptors: hi / lo plane of the matrix at float offset `off` with `rows` rows and K columns
+    auto wd = [&](int off, int rows) { return umma::desc_lo32(img_s + (uint32_t)off * 4u, (uint32_t)rows); };
     for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-      int g = find_segment(tile_ptr, n_graphs, unit);
-      int O = obs_ptr[g + 1] - obs_ptr[g];
-      O = __shfl_sync(0xffffffffu, O, 0);
+      if (unit != cur_unit) {
+        cur_unit = unit;
+        meta_cur = meta_next;
+        meta_next = load_meta(unit + gridDim.x);
+      }
+      const int O = meta_cur.z;
       const int nch = n_blocks ? tc_nchunks(O) : 0, per = tc_per(O, nch);
       // one stage for both tiles: wait for the tile's operands, issue, commit
-#define GMP_TC_STAGE(BODY)                                                        \
+#ifdef GMP_TC_PROFILE
+#define GMP_TC_T0 const long long w0 = clock64();
+#define GMP_TC_T1 prof_ready[t] += clock64() - w0;
+#define GMP_TC_I0 const long long i0 = clock64();
+#define GMP_TC_I1(KIND) prof_issue[KIND] += clock64() - i0;
+#else
+#define GMP_TC_T0
+#define GMP_TC_T1
+#define GMP_TC_I0
+#define GMP_TC_I1(KIND)
+#endif
+#define GMP_TC_STAGE(KIND, ...)                                                   \
   _Pragma("unroll") for (int t = 0; t < 2; ++t) {                                 \
+    GMP_TC_T0                                                                     \
     umma::mbar_wait_guard(&bar_ready[t], rph[t]);                                 \
+    GMP_TC_T1                                                                     \
     rph[t] ^= 1u;                                                                 \
     umma::fence_after_sync();                                                     \
     if (umma::elect_one()) {                                                      \
       const uint32_t tc = tm_u + (uint32_t)t * 256u;                              \
-      BODY;                                                                       \
+      const uint32_t xh = tc + Cf::cXH, xl = tc + Cf::cXL;                        \
+      GMP_TC_I0                                                                   \
+      __VA_ARGS__;                                                                \
       umma::commit(&bar_done[t]);                                                 \
+      GMP_TC_I1(KIND)                                                             \
     }                                                                             \
     __syncwarp();                                                                 \
   }
-      GMP_TC_STAGE(umma::gemm3_ts(tc + Cf::cA1, tc + Cf::cXH, tc + Cf::cXL, b_hi(Cf::EF0), b_hi(Cf::EF0 + E * K0), E, 0, E, K0, false));
-      GMP_TC_STAGE(umma::gemm3_ts(tc + Cf::cA1, tc + Cf::cXH, tc + Cf::cXL, b_hi(Cf::EF2), b_hi(Cf::EF2 + E * E), E, 0, E, E, false));
+      if constexpr (!Cf::kSimtIn) {   // hidden layer of edge_free_code on the tensor cores (rows 0..31 of the stacked ENC0)
+        GMP_TC_STAGE(0, (umma::gemm3_fixed<E, K0, 64>(tc + Cf::cA1, xh, xl, wd(Cf::ENC0, 64), wd(Cf::ENC0 + 64 * K0, 64), false)));
+      }
+      GMP_TC_STAGE(1, (umma::gemm3_fixed<E, E, E>(tc + Cf::cA1, xh, xl, wd(Cf::EF2, E), wd(Cf::EF2 + E * E, E), false)));
       for (int blk = 0; blk < n_blocks; ++blk) {
         const int wb = Cf::BLK + blk * Cf::kBlk;
+        const uint32_t gv_h = wd(wb, 64), gv_l = wd(wb + 64 * E, 64);
         if (nch == 0) {
-          GMP_TC_STAGE(umma::gemm3_ts(tc + Cf::cA1, tc + Cf::cXH, tc + Cf::cXL, b_hi(wb), b_hi(wb + 64 * E), 64, 0, 64, E, false));
+          GMP_TC_STAGE(2, (umma::gemm3_fixed<64, E, 64>(tc + Cf::cA1, xh, xl, gv_h, gv_l, false)));
         }
-        for (int c = 0; c < nch; ++c) {
-          umma::mbar_wait_guard(&bar_tabfull, full_ph);   // this (blk, chunk)'s tables have landed
+        for (int sc = 0; 2 * sc < nch; ++sc) {
+          const int ns = min(2, nch - 2 * sc);
+          if (sc > 0) {
+            // more than 128 obstacles (rare): both tiles have retired the previous table's products once they publish the
+            // restored A operand; only then may the buffer be refilled
+            umma::mbar_wait_guard(&bar_ready[0], rph[0]); rph[0] ^= 1u;
+            umma::mbar_wait_guard(&bar_ready[1], rph[1]); rph[1] ^= 1u;
+            tab_busy = false;
+            cursor_load();
+          }
+#ifdef GMP_TC_PROFILE
+          const long long wt0 = clock64();
+#endif
+          umma::mbar_wait_guard(&bar_tabfull, full_ph);   // this table has landed
           full_ph ^= 1u;
-          const uint32_t mt_hi = tab_s, mt_lo = tab_s + (uint32_t)(E * per) * 4u, vt_hi = tab_s + (uint32_t)(2 * E * per) * 4u,
-                         vt_lo = tab_s + (uint32_t)(3 * E * per) * 4u;
-          GMP_TC_STAGE({
-            if (c == 0) umma::gemm3_ts(tc + Cf::cA1, tc + Cf::cXH, tc + Cf::cXL, b_hi(wb), b_hi(wb + 64 * E), 64, 0, 64, E, false);
-            umma::gemm3_ts(tc + Cf::cSC, tc + Cf::cXH, tc + Cf::cXL, mt_hi, mt_lo, per, 0, per, E, false);
-          });
-          GMP_TC_STAGE(umma::gemm3_ts(tc + Cf::cPV, tc + Cf::cSC, tc + Cf::cPL, vt_hi, vt_lo, E, 0, E, per, false));
-          // both tiles' P.V issued: when they retire the table buffer is free -> refill with the next table
-          if (umma::elect_one()) umma::commit(&bar_tabfree);
-          __syncwarp();
-          umma::mbar_wait_guard(&bar_tabfree, free_ph);
-          free_ph ^= 1u;
-          cursor_load();
+#ifdef GMP_TC_PROFILE
+          prof_tab += clock64() - wt0;
+#endif
+          const uint32_t sub = (uint32_t)(4 * E * per) * 4u, pl = (uint32_t)(E * per) * 4u;   // bytes per sub-chunk / per plane
+          const uint32_t mt_h0 = umma::desc_lo32(tab_s, (uint32_t)per), mt_l0 = umma::desc_lo32(tab_s + pl, (uint32_t)per),
+                         vt_h0 = umma::desc_lo32(tab_s + 2 * pl, E), vt_l0 = umma::desc_lo32(tab_s + 3 * pl, E);
+          const uint32_t mt_h1 = umma::desc_lo32(tab_s + sub, (uint32_t)per), mt_l1 = umma::desc_lo32(tab_s + sub + pl, (uint32_t)per),
+                         vt_h1 = umma::desc_lo32(tab_s + sub + 2 * pl, E), vt_l1 = umma::desc_lo32(tab_s + sub + 3 * pl, E);
+          if (sc == 0) {
+            GMP_TC_STAGE(2, {
+              umma::gemm3_fixed<64, E, 64>(tc + Cf::cA1, xh, xl, gv_h, gv_l, false);
+              umma::gemm3_n<E>(tc + Cf::cSC, xh, xl, mt_h0, mt_l0, per);
+              if (ns == 2) umma::gemm3_n<E>(tc + Cf::cSC1, xh, xl, mt_h1, mt_l1, per);
+            });
+          } else {
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {   // (the tiles' `ready` phases were consumed above)
+              umma::fence_after_sync();
+              if (umma::elect_one()) {
+                const uint32_t tc = tm_u + (uint32_t)t * 256u;
+                umma::gemm3_n<E>(tc + Cf::cSC, tc + Cf::cXH, tc + Cf::cXL, mt_h0, mt_l0, per);
+                if (ns == 2) umma::gemm3_n<E>(tc + Cf::cSC1, tc + Cf::cXH, tc + Cf::cXL, mt_h1, mt_l1, per);
+                umma::commit(&bar_done[t]);
+              }
+              __syncwarp();
+            }
+          }
+          GMP_TC_STAGE(3, (umma::gemm3_k<E, E>(tc + (ns == 2 ? Cf::cPV2 : Cf::cPV1), tc + Cf::cSC, tc + Cf::cPL, vt_h0, vt_l0, per)));
+          if (ns == 2) {
+            GMP_TC_STAGE(3, (umma::gemm3_k<E, E>(tc + Cf::cPV2, tc + Cf::cSC1, tc + Cf::cPL, vt_h1, vt_l1, per)));
+          }
         }
-        GMP_TC_STAGE(umma::gemm3_ts(tc + Cf::cA1, tc + Cf::cXH, tc + Cf::cXL, b_hi(wb + Cf::oW1), b_hi(wb + Cf::oW1 + E * E), E, 0, E, E, false));
-        GMP_TC_STAGE(umma::gemm3_ts(tc + Cf::cA1, tc + Cf::cXH, tc + Cf::cXL, b_hi(wb + Cf::oW2), b_hi(wb + Cf::oW2 + E * E), E, 0, E, E, false));
+        GMP_TC_STAGE(1, (umma::gemm3_fixed<E, E, E>(tc + Cf::cA1, xh, xl, wd(wb + Cf::oW1, E), wd(wb + Cf::oW1 + E * E, E), false)));
+        // both tiles have published map_feed.w_1's operand, so every P.V of this block has retired: refill the table buffer
+        // (next block / next unit) behind the two FFN stages
+        if (nch > 0) tab_busy = false;
+        cursor_load();
+        GMP_TC_STAGE(1, (umma::gemm3_fixed<E, E, E>(tc + Cf::cA1, xh, xl, wd(wb + Cf::oW2, E), wd(wb + Cf::oW2 + E * E, E), false)));
       }
-      GMP_TC_STAGE(umma::gemm3_ts(tc + Cf::cA1, tc + Cf::cXH, tc + Cf::cXL, b_hi(Cf::QP), b_hi(Cf::QP + 64 * E), 64, 0, 64, E, false));
-      GMP_TC_STAGE(umma::gemm3_ts(tc + Cf::cSC, tc + Cf::cXH, tc + Cf::cXL, b_hi(Cf::EC0), b_hi(Cf::EC0 + E * K0), E, 0, E, K0, false));
-      GMP_TC_STAGE(umma::gemm3_ts(tc + Cf::cSC, tc + Cf::cXH, tc + Cf::cXL, b_hi(Cf::EC2), b_hi(Cf::EC2 + E * E), E, 0, E, E, false));
-      GMP_TC_STAGE(umma::gemm3_ts(tc + Cf::cA1 + 32, tc + Cf::cXH, tc + Cf::cXL, b_hi(Cf::W5), b_hi(Cf::W5 + E * E), E, 0, E, E, true));
+      if constexpr (!Cf::kSimtIn) {   // hidden layer of edge_code: rows 32..63 of ENC0, inputs staged at cHH / cHL
+        GMP_TC_STAGE(0, (umma::gemm3_fixed<E, K0, 64>(tc + Cf::cSC, tc + Cf::cHH, tc + Cf::cHL, wd(Cf::ENC0, 64) + E,
+                                                      wd(Cf::ENC0 + 64 * K0, 64) + E, false)));
+      }
+      // Q | P_ef = [Wc ; W4] ef, then P += (W5 W_ec2) hidden_ec
+      GMP_TC_STAGE(4, {
+        umma::gemm3_fixed<64, E, 64>(tc + Cf::cA1, xh, xl, wd(Cf::QP, 64), wd(Cf::QP + 64 * E, 64), false);
+        umma::gemm3_fixed<E, E, E>(tc + Cf::cA1 + 32, tc + Cf::cHH, tc + Cf::cHL, wd(Cf::W52, E), wd(Cf::W52 + E * E, E), true);
+      });
 #undef GMP_TC_STAGE
     }
+#ifdef GMP_TC_PROFILE
+    if (blockIdx.x == 0 && (threadIdx.x & 31) == 0)
+      printf("tc profile: issuer total %lld cyc; waiting ready[0] %lld ready[1] %lld tables %lld (unused %lld); issuing: enc0 %lld 32x32 %lld "
+             "GV+scores %lld PV %lld QP %lld\n", clock64() - prof_t0, prof_ready[0], prof_ready[1], prof_tab, prof_free, prof_issue[0],
+             prof_issue[1], prof_issue[2], prof_issue[3], prof_issue[4]);
+#endif
   } else {
     // =================================================================== compute warps: thread == edge row
     const int tile = warp_u >> 2;
@@ -262,20 +369,57 @@ __global__ void __launch_bounds__(384, 1) edge_feature_tc_kernel(
       umma::fence_before_sync();
       umma::mbar_arrive(&bar_ready[tile]);
     };
-    auto await = [&]() {
+#ifdef GMP_TC_PROFILE
+    long long prof_wait = 0, prof_t0 = clock64();
+#endif
+#ifdef GMP_TC_PROFILE
+    long long prof_w[6] = {0, 0, 0, 0, 0, 0}, prof_e[6] = {0, 0, 0, 0, 0, 0}, prof_last = clock64();
+    int prof_kind = 5;
+#endif
+    auto await = [&](int kind = 5) {   // kind (profiling only): 0 Gx|Vx+scores, 1 P.V, 2 w_1, 3 w_2, 4 tail, 5 encoders / other
+#ifdef GMP_TC_PROFILE
+      const long long w0 = clock64();
+      prof_e[prof_kind] += w0 - prof_last;   // work since the previous await belongs to that stage's epilogue
+#endif
       umma::mbar_wait_guard(&bar_done[tile], dph);
       dph ^= 1u;
       umma::fence_after_sync();
+#ifdef GMP_TC_PROFILE
+      prof_last = clock64();
+      prof_wait += prof_last - w0;
+      prof_w[kind] += prof_last - w0;
+      prof_kind = kind;
+#endif
     };
+    // this unit's metadata and edge endpoints are fetched one unit ahead (their latency hides behind the previous unit)
+    int4 meta_nx = make_int4(0, 0, 0, 0);
+    int s_nx = 0, d_nx = 0;
+    auto prefetch_unit = [&](int u) {
+      if (u < n_units) {
+        meta_nx = __ldg(unit_meta + u);
+        const int sl = meta_nx.x + tile * 128 + row;
+        const bool ok = sl < meta_nx.y;
+        s_nx = ok ? __ldg(csr_src + sl) : 0;
+        d_nx = ok ? __ldg(csr_dst + sl) : 0;
+      }
+    };
+    prefetch_unit(blockIdx.x);
+    // The issuer serves the tiles alternately, so whatever head start tile 0 has over tile 1 persists for the whole kernel.
+    // Starting tile 1 about half an epilogue late puts the tiles in anti-phase: one tile's tcgen05.ld / st traffic then
+    // overlaps the other tile's ALU work instead of both queueing on the TMEM port at the same time.
+    if (tile == 1 && phase_delay > 0) {
+      const long long t_go = clock64() + phase_delay;
+      while (clock64() < t_go) {}
+    }
     for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-      const int g = find_segment(tile_ptr, n_graphs, unit);
-      const int slot = edge_ptr[g] + (unit - tile_ptr[g]) * 256 + tile * 128 + row;
-      const bool valid = slot < edge_ptr[g + 1];
-      const int O = obs_ptr[g + 1] - obs_ptr[g];
+      const int4 meta = meta_nx;
+      const int slot = meta.x + tile * 128 + row;
+      const bool valid = slot < meta.y;
+      const int O = meta.z;
       const int nch = n_blocks ? tc_nchunks(O) : 0, per = tc_per(O, nch);
-      const int s_node = valid ? csr_src[slot] : 0, d_node = valid ? csr_dst[slot] : 0;
-      auto stage_inputs = [&]() {   // cat(v[src], v[dst]) zero padded to K0 -> XH / XL
-        float in[K0];
+      const int s_node = s_nx, d_node = d_nx;
+      prefetch_unit(unit + gridDim.x);
+      auto gather = [&](float* in) {   // cat(v[src], v[dst]), zero padded to K0
 #pragma unroll
         for (int k = 0; k < K0; ++k) in[k] = 0.f;
 #pragma unroll
@@ -283,17 +427,51 @@ __global__ void __launch_bounds__(384, 1) edge_feature_tc_kernel(
           in[k] = __ldg(v + (size_t)s_node * C + k);
           in[C + k] = __ldg(v + (size_t)d_node * C + k);
         }
-        umma::st_split<K0>(tc + Cf::cXH, tc + Cf::cXL, in);
+      };
+      // hidden = relu(W in + b) of encoder `which` (0 edge_free_code.0, 1 edge_code.0) as plain FMAs (2C <= 8)
+      auto simt_hidden = [&](const float* in, int which, float* h) {
+        const float* Wf = img + Cf::ENC0F + which * 32 * Cf::K4;
+        const float* bb = vec + (which ? Cf::vEC0b : Cf::vEF0b);
+#pragma unroll
+        for (int n = 0; n < E; ++n) {
+          float a = bb[n];
+#pragma unroll
+          for (int k4 = 0; k4 < Cf::K4; k4 += 4) {
+            const float4 w = *reinterpret_cast<const float4*>(Wf + n * Cf::K4 + k4);
+            a = fmaf(w.x, in[k4], a); a = fmaf(w.y, in[k4 + 1], a); a = fmaf(w.z, in[k4 + 2], a); a = fmaf(w.w, in[k4 + 3], a);
+          }
+          h[n] = fmaxf(a, 0.f);
+        }
+      };
+      // A operand of the tail: hidden layer of edge_code (SIMT) or its inputs (tensor-core first layer) -> cHH / cHL
+      auto stage_edge_code = [&]() {
+        float in[K0];
+        gather(in);
+        if constexpr (Cf::kSimtIn) {
+          float h[E];
+          simt_hidden(in, 1, h);
+          umma::st_split<E>(tc + Cf::cHH, tc + Cf::cHL, h);
+        } else {
+          umma::st_split<K0>(tc + Cf::cHH, tc + Cf::cHL, in);
+        }
       };
       float x[E];
       // ---- edge_free_code                                                  (model.py:123)
-      stage_inputs();
-      publish();
-      await();
-      tc_detail::ld_cols<E>(tc + Cf::cA1, x);
-      umma::wait_ld();
+      {
+        float in[K0];
+        gather(in);
+        if constexpr (Cf::kSimtIn) {
+          simt_hidden(in, 0, x);
+        } else {
+          umma::st_split<K0>(tc + Cf::cXH, tc + Cf::cXL, in);
+          publish();
+          await();
+          tc_detail::ld_cols<E>(tc + Cf::cA1, x);
+          umma::wait_ld();
 #pragma unroll
-      for (int n = 0; n < E; ++n) x[n] = fmaxf(x[n] + vec[Cf::vEF0b + n], 0.f);
+          for (int n = 0; n < E; ++n) x[n] = fmaxf(x[n] + vec[Cf::vEF0b + n], 0.f);
+        }
+      }
       umma::st_split<E>(tc + Cf::cXH, tc + Cf::cXL, x);
       publish();
       await();
@@ -302,73 +480,89 @@ __global__ void __launch_bounds__(384, 1) edge_feature_tc_kernel(
 #pragma unroll
       for (int n = 0; n < E; ++n) x[n] += vec[Cf::vEF2b + n];
       umma::st_split<E>(tc + Cf::cXH, tc + Cf::cXL, x);
+      if (n_blocks == 0) stage_edge_code();
       publish();
       // ---- three edge Blocks                                               (model.py:130, 153-218)
       for (int blk = 0; blk < n_blocks; ++blk) {
         const float* bv = vec + Cf::vBLK + blk * 192;
         float acc[E];
         float m, l = 1.0f;
-        await();   // Gx | Vx (+ scores of chunk 0)
+        await(0);   // Gx | Vx (+ scores of the first one or two sub-chunks)
         {
           float u[E];
           tc_detail::ld_cols<E>(tc + Cf::cA1, u);
-          tc_detail::ld_cols<E>(tc + Cf::cA1 + 32, acc);
+          tc_detail::ld_cols<E>(tc + Cf::cA1 + 32, acc);   // value of the row itself, weight exp2(s_self - m) = 1
           umma::wait_ld();
-          float s = 0.f;
+          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;               // self score x^T G x   (model.py:175,177)
 #pragma unroll
-          for (int n = 0; n < E; ++n) s = fmaf(u[n], x[n], s);   // self score x^T G x   (model.py:175,177)
-          m = s;
-        }
-        for (int c = 0; c < nch; ++c) {
-          if (c > 0) {
-            // the probabilities' lo plane overwrote XH / XL: restore the A operand for this chunk's scores
-            umma::st_split<E>(tc + Cf::cXH, tc + Cf::cXL, x);
-            publish();
-            await();
+          for (int n = 0; n < E; n += 4) {
+            s0 = fmaf(u[n], x[n], s0); s1 = fmaf(u[n + 1], x[n + 1], s1); s2 = fmaf(u[n + 2], x[n + 2], s2); s3 = fmaf(u[n + 3], x[n + 3], s3);
           }
-          const int cnt = min(per, O - c * per);
-          float sc[Cf::kOcMax];
+          m = (s0 + s1) + (s2 + s3);
+        }
+        // online softmax over one sub-chunk: scores at TMEM column `col` -> probabilities (hi plane in place, lo plane at
+        // cPL); returns the factor by which everything accumulated so far must be rescaled
+        auto softmax_sub = [&](uint32_t col, int cnt) -> float {
+          constexpr int W = Cf::kOcMax;
+          float sc[W];
 #pragma unroll
-          for (int j = 0; j < Cf::kOcMax; j += 16)
-            if (j < per) umma::ld16(tc + Cf::cSC + j, sc + j);
+          for (int j = 0; j < W; j += 16)
+            if (j < per) umma::ld16(tc + col + j, sc + j);
           umma::wait_ld();
           // padded table rows score 0: mask them to -inf (weight 0); only the 16-column pieces at / after `cnt`
 #pragma unroll
-          for (int j = 0; j < Cf::kOcMax; j += 16)
+          for (int j = 0; j < W; j += 16)
             if (j < per && j + 16 > cnt) {
 #pragma unroll
               for (int i = 0; i < 16; ++i)
                 if (j + i >= cnt) sc[j + i] = -INFINITY;
             }
-          float mnew = m;
+          float m0 = m, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;   // four independent chains (ILP)
 #pragma unroll
-          for (int j = 0; j < Cf::kOcMax; j += 16)
+          for (int j = 0; j < W; j += 16)
             if (j < per) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) mnew = fmaxf(mnew, sc[j + i]);
-            }
-          const float corr = umma::ex2_approx(m - mnew);
-          float lsum = l * corr;
-#pragma unroll
-          for (int j = 0; j < Cf::kOcMax; j += 16)
-            if (j < per) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const float p = umma::ex2_approx(sc[j + i] - mnew);
-                lsum += p;
-                sc[j + i] = p;
+              for (int i = 0; i < 16; i += 4) {
+                m0 = fmaxf(m0, sc[j + i]); m1 = fmaxf(m1, sc[j + i + 1]); m2 = fmaxf(m2, sc[j + i + 2]); m3 = fmaxf(m3, sc[j + i + 3]);
               }
-              umma::st_split<16>(tc + Cf::cSC + j, tc + Cf::cPL + j, sc + j);
             }
-          l = lsum;
-          m = mnew;
-          publish();
-          await();   // P.V of this chunk
-          float pv[E];
-          tc_detail::ld_cols<E>(tc + Cf::cPV, pv);
-          umma::wait_ld();
+          const float mnew = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+          const float corr = umma::ex2_approx(m - mnew);
+          float l0 = l * corr, l1 = 0.f, l2 = 0.f, l3 = 0.f;
 #pragma unroll
-          for (int n = 0; n < E; ++n) acc[n] = fmaf(acc[n], corr, pv[n]);
+          for (int j = 0; j < W; j += 16)
+            if (j < per) {
+#pragma unroll
+              for (int i = 0; i < 16; i += 4) {
+                const float p0 = umma::ex2_approx(sc[j + i] - mnew), p1 = umma::ex2_approx(sc[j + i + 1] - mnew),
+                            p2 = umma::ex2_approx(sc[j + i + 2] - mnew), p3 = umma::ex2_approx(sc[j + i + 3] - mnew);
+                l0 += p0; l1 += p1; l2 += p2; l3 += p3;
+                sc[j + i] = p0; sc[j + i + 1] = p1; sc[j + i + 2] = p2; sc[j + i + 3] = p3;
+              }
+              umma::st_split<16>(tc + col + j, tc + Cf::cPL + j, sc + j);
+            }
+          l = (l0 + l1) + (l2 + l3);
+          m = mnew;
+          return corr;
+        };
+        for (int s2 = 0; 2 * s2 < nch; ++s2) {
+          const int ns = min(2, nch - 2 * s2);
+          if (s2 > 0) {
+            // (> 128 obstacles) the probabilities' lo plane overwrote XH / XL: restore the A operand for these scores
+            umma::st_split<E>(tc + Cf::cXH, tc + Cf::cXL, x);
+            publish();
+            await();
+          }
+          for (int sub = 0; sub < ns; ++sub) {
+            const float corr = softmax_sub(sub ? Cf::cSC1 : Cf::cSC, max(0, min(per, O - (2 * s2 + sub) * per)));
+            publish();   // -> P.V of this sub-chunk
+            await(1);
+            float pv[E];
+            tc_detail::ld_cols<E>(tc + (ns == 2 ? Cf::cPV2 : Cf::cPV1), pv);
+            umma::wait_ld();
+#pragma unroll
+            for (int n = 0; n < E; ++n) acc[n] = fmaf(acc[n], corr, pv[n]);
+          }
         }
         // softmax normalisation, residual, attention.layer_norm               (model.py:181)
         {
@@ -379,61 +573,59 @@ __global__ void __launch_bounds__(384, 1) edge_feature_tc_kernel(
         tc_detail::layernorm_row<E>(acc, bv, bv + 32, 1e-6f);
         umma::st_split<E>(tc + Cf::cXH, tc + Cf::cXL, acc);
         publish();
-        await();   // map_feed.w_1                                             (model.py:193-201)
+        await(2);   // map_feed.w_1                                             (model.py:193-201)
         tc_detail::ld_cols<E>(tc + Cf::cA1, x);
         umma::wait_ld();
 #pragma unroll
         for (int n = 0; n < E; ++n) x[n] = fmaxf(x[n] + bv[64 + n], 0.f);
         umma::st_split<E>(tc + Cf::cXH, tc + Cf::cXL, x);
         publish();
-        await();   // map_feed.w_2
+        await(3);   // map_feed.w_2
         tc_detail::ld_cols<E>(tc + Cf::cA1, x);
         umma::wait_ld();
 #pragma unroll
         for (int n = 0; n < E; ++n) x[n] += bv[96 + n] + acc[n];
         tc_detail::layernorm_row<E>(x, bv + 128, bv + 160, 1e-6f);
         umma::st_split<E>(tc + Cf::cXH, tc + Cf::cXL, x);
+        if (blk == n_blocks - 1) stage_edge_code();
         publish();
       }
-      // ---- Q = Wc ef + b ; P_ef = W4 ef (stays in TMEM)                      (model.py:145-146 ; :39)
-      await();
-      tc_detail::ld_cols<E>(tc + Cf::cA1, x);
-      umma::wait_ld();
-      if (valid) {
-        float4* q4 = reinterpret_cast<float4*>(Q + (size_t)slot * E);
+      // ---- hidden layer of edge_code on the tensor cores (wide inputs)     (model.py:120)
+      if constexpr (!Cf::kSimtIn) {
+        await();
+        float h[E];
+        tc_detail::ld_cols<E>(tc + Cf::cSC, h);
+        umma::wait_ld();
 #pragma unroll
-        for (int n = 0; n < E; n += 4)
-          q4[n >> 2] = make_float4(x[n] + vec[Cf::vQb + n], x[n + 1] + vec[Cf::vQb + n + 1], x[n + 2] + vec[Cf::vQb + n + 2],
-                                   x[n + 3] + vec[Cf::vQb + n + 3]);
+        for (int n = 0; n < E; ++n) h[n] = fmaxf(h[n] + vec[Cf::vEC0b + n], 0.f);
+        umma::st_split<E>(tc + Cf::cHH, tc + Cf::cHL, h);
+        publish();
       }
-      // ---- edge_code                                                       (model.py:120)
-      stage_inputs();
-      publish();
-      await();
-      tc_detail::ld_cols<E>(tc + Cf::cSC, x);
-      umma::wait_ld();
-#pragma unroll
-      for (int n = 0; n < E; ++n) x[n] = fmaxf(x[n] + vec[Cf::vEC0b + n], 0.f);
-      umma::st_split<E>(tc + Cf::cXH, tc + Cf::cXL, x);
-      publish();
-      await();
-      tc_detail::ld_cols<E>(tc + Cf::cSC, x);
-      umma::wait_ld();
-#pragma unroll
-      for (int n = 0; n < E; ++n) x[n] += vec[Cf::vEC2b + n];
-      umma::st_split<E>(tc + Cf::cXH, tc + Cf::cXL, x);
-      publish();
-      await();   // P = W4 ef + W5 ec
+      // ---- Q = Wc ef + b (model.py:145-146);  P = W4 ef + W5 edge_code + b (model.py:39), edge_code.2 folded into W5
+      await(4);
+      float q[E];
+      tc_detail::ld_cols<E>(tc + Cf::cA1, q);
       tc_detail::ld_cols<E>(tc + Cf::cA1 + 32, x);
       umma::wait_ld();
       if (valid) {
+        float4* q4 = reinterpret_cast<float4*>(Q + (size_t)slot * E);
         float4* p4 = reinterpret_cast<float4*>(P + (size_t)slot * E);
 #pragma unroll
-        for (int n = 0; n < E; n += 4)
+        for (int n = 0; n < E; n += 4) {
+          q4[n >> 2] = make_float4(q[n] + vec[Cf::vQb + n], q[n + 1] + vec[Cf::vQb + n + 1], q[n + 2] + vec[Cf::vQb + n + 2],
+                                   q[n + 3] + vec[Cf::vQb + n + 3]);
           p4[n >> 2] = make_float4(x[n] + vec[Cf::vPb + n], x[n + 1] + vec[Cf::vPb + n + 1], x[n + 2] + vec[Cf::vPb + n + 2],
                                    x[n + 3] + vec[Cf::vPb + n + 3]);
+        }
       }
     }
+#ifdef GMP_TC_PROFILE
+    if (blockIdx.x == 0 && row == 0)
+      printf("tc profile: tile %d total %lld cyc, waiting for MMAs %lld cyc (%d units); wait/epilogue per stage kind: A %lld/%lld PV %lld/%lld "
+             "w1 %lld/%lld w2 %lld/%lld tail %lld/%lld enc %lld/%lld\n", tile, clock64() - prof_t0, prof_wait,
+             (n_units + gridDim.x - 1) / gridDim.x, prof_w[0], prof_e[0], prof_w[1], prof_e[1], prof_w[2], prof_e[2], prof_w[3], prof_e[3],
+             prof_w[4], prof_e[4], prof_w[5], prof_e[5]);
+#endif
   }
   umma::fence_before_sync();
   __syncthreads();

@@ -129,9 +129,9 @@ __device__ __forceinline__ void st32(uint32_t taddr, const float* r) {
 // TF32 split of an fp32 value: hi = round-to-nearest TF32 of x, lo = round-to-nearest TF32 of the (exact) remainder.
 // Rounding (instead of letting the tensor core truncate the operands) keeps the split error unbiased at ~2^-23 |x|.
 __device__ __forceinline__ float tf32_rna(float x) {
-  uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-  return __uint_as_float(u);
+  // (cvt.rna.tf32.f32 costs four SASS instructions because it special-cases NaN; the bit trick is two and maps
+  //  +-inf to itself, which is all the epilogues can produce)
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 __device__ __forceinline__ float tf32_hi(float x) { return tf32_rna(x); }
 
@@ -169,7 +169,7 @@ __device__ __forceinline__ void mbar_wait_guard(uint64_t* bar, uint32_t phase) {
   const uint32_t addr = smem_u32(bar);
   uint32_t done = 0, spins = 0;
   while (true) {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x4000;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                  : "=r"(done)
                  : "r"(addr), "r"(phase)
                  : "memory");
@@ -178,9 +178,59 @@ __device__ __forceinline__ void mbar_wait_guard(uint64_t* bar, uint32_t phase) {
   }
 }
 
-// 3xTF32 product with A in TMEM (hi / lo column planes) and B in shared memory (hi / lo K-major planes of
-// B_ROWS x K floats): D[128 x N] (+)= A[128 x K] . B[N x K]^T.   One thread issues; K % 8 == 0.
-// `b_rows` is the row count the B planes were laid out with (>= N; the MMA reads rows [b_row0, b_row0 + N)).
+// ---- 3xTF32 products with A in TMEM (hi / lo column planes) and B in shared memory (hi / lo K-major planes):
+// D[128 x N] (+)= A[128 x K] . B[N x K]^T.  One elected thread issues; everything it touches should be warp-uniform
+// so that the descriptors live in uniform registers and the UTCHMMA instructions issue back to back.
+//
+// A no-swizzle K-major descriptor is { hi word = 0x4008 (stride byte offset 128 B, version 1),
+//                                      lo word = (shared address >> 4) | (B_ROWS << 16)  (leading byte offset = B_ROWS*16 B) }
+// and advancing by one K step of 8 adds 2*B_ROWS to the lo word.
+__device__ __forceinline__ uint32_t desc_lo32(uint32_t saddr, uint32_t b_rows) { return ((saddr & 0x3FFFFu) >> 4) | (b_rows << 16); }
+__device__ __forceinline__ uint64_t desc64(uint32_t lo32) { return ((uint64_t)0x4008u << 32) | (uint64_t)lo32; }
+
+// compile-time shape (weights): fully unrolled
+template <int N, int K, int B_ROWS>
+__device__ __forceinline__ void gemm3_fixed(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t bh_lo32, uint32_t bl_lo32,
+                                            bool accumulate) {
+  constexpr uint32_t id = idesc_tf32(128, N);
+#pragma unroll
+  for (int ks = 0; ks < K / 8; ++ks) {
+    const uint64_t bh = desc64(bh_lo32 + (uint32_t)(ks * 2 * B_ROWS)), bl = desc64(bl_lo32 + (uint32_t)(ks * 2 * B_ROWS));
+    mma_ts(d_tmem, a_lo + ks * 8, bh, id, (ks > 0 || accumulate) ? 1u : 0u);
+    mma_ts(d_tmem, a_hi + ks * 8, bl, id, 1u);
+    mma_ts(d_tmem, a_hi + ks * 8, bh, id, 1u);
+  }
+}
+// runtime N (scores against `n` obstacle rows laid out with b_rows = n), K compile time
+template <int K>
+__device__ __forceinline__ void gemm3_n(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t bh_lo32, uint32_t bl_lo32, int n) {
+  const uint32_t id = idesc_tf32(128, n);
+  const uint32_t step = 2u * (uint32_t)n;
+#pragma unroll
+  for (int ks = 0; ks < K / 8; ++ks) {
+    const uint64_t bh = desc64(bh_lo32 + ks * step), bl = desc64(bl_lo32 + ks * step);
+    mma_ts(d_tmem, a_lo + ks * 8, bh, id, ks > 0 ? 1u : 0u);
+    mma_ts(d_tmem, a_hi + ks * 8, bl, id, 1u);
+    mma_ts(d_tmem, a_hi + ks * 8, bh, id, 1u);
+  }
+}
+// runtime K (probabilities . values), N and B_ROWS compile time
+template <int N, int B_ROWS>
+__device__ __forceinline__ void gemm3_k(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t bh_lo32, uint32_t bl_lo32, int k) {
+  constexpr uint32_t id = idesc_tf32(128, N);
+  uint32_t acc = 0u;
+#pragma unroll 2
+  for (int ks = 0; ks < k / 8; ++ks) {
+    const uint64_t bh = desc64(bh_lo32), bl = desc64(bl_lo32);
+    mma_ts(d_tmem, a_lo, bh, id, acc);
+    mma_ts(d_tmem, a_hi, bl, id, 1u);
+    mma_ts(d_tmem, a_hi, bh, id, 1u);
+    acc = 1u;
+    a_hi += 8; a_lo += 8; bh_lo32 += 2 * B_ROWS; bl_lo32 += 2 * B_ROWS;
+  }
+}
+
+// generic runtime-shape version (bring-up / microbenchmark)
 __device__ __forceinline__ void gemm3_ts(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi_saddr, uint32_t b_lo_saddr,
                                          int b_rows, int b_row0, int N, int K, bool accumulate) {
   const uint32_t id = idesc_tf32(128, N);

@@ -555,6 +555,18 @@ def main():
     # + the CSR (src, dst) ids (8 B/edge).  The gathered A[src] / B[dst] rows (2*e*4 B/edge) are L2-resident (2 x 33 MB
     # per 256-graph batch) and are NOT counted.
     msg_bytes = et * (wl["e"] * 4 + 8)
+    if wl["e"] == 32:
+        # tcgen05 path: 3xTF32 (three kind::tf32 MMAs per product, fp32 accumulate in TMEM).  TF32 dense runs at half the bf16
+        # rate and every product is issued three times, so the ceiling of this arithmetic is peak/6 of the bf16 figure.
+        ef_kernel = "edge_feature_tc_kernel<%d>" % c
+        ef_note = ("tcgen05.mma kind::tf32, 3xTF32 split operands (1e-4 logit tolerance rules out 1-pass TF32/BF16), A operands and "
+                   "accumulators in TMEM; against the 3xTF32 ceiling (bf16 peak / 6 = %.0f TFLOP/s) the fraction is %.3f; the fp32 SIMT "
+                   "kernel it replaces peaked at 148 SM x 128 FMA x %.0f MHz = %.1f TFLOP/s"
+                   % (peak_tf / 6.0, ef_tflops / (peak_tf / 6.0), sm_mhz, fp32_peak_tf))
+    else:
+        ef_kernel = "edge_feature_kernel<%d,%d>" % (c, wl["e"])
+        ef_note = ("fp32 FMA kernel (1e-4 logit tolerance rules out 1-pass TF32/BF16; the tcgen05 3xTF32 stage exists for e = 32); vs "
+                   "fp32 SIMT peak 148 SM x 128 FMA x %.0f MHz = %.1f TFLOP/s the fraction is %.3f" % (sm_mhz, fp32_peak_tf, ef_tflops / fp32_peak_tf))
     line = {
         "metric": "explorer_graphs_per_sec", "value": graphs_per_s, "unit": "graphs/s", "n_gpus": world, "steps": K,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -567,12 +579,11 @@ def main():
         "collision_free_edge_fraction": float(state["rows"][:, 2].sum()) / et,
         "knn_graphs_per_sec": B * world / (phase_ms["knn_graph"] / K / 1e3),
         "forward_tflops_ref_oplist": fwd_flops / (phase_ms["explorer_forward"] / K / 1e3) / 1e12,
-        "roofline": {"kernel": "edge_feature_kernel<%d,%d>" % (c, wl["e"]), "bound": "tensor", "achieved": ef_tflops, "peak": peak_tf,
-                     "unit": "TFLOP/s", "frac": ef_tflops / peak_tf, "traffic": traffic_of("edge_feature_kernel<%d,%d>" % (c, wl["e"])),
+        "roofline": {"kernel": ef_kernel, "bound": "tensor", "achieved": ef_tflops, "peak": peak_tf,
+                     "unit": "TFLOP/s", "frac": ef_tflops / peak_tf, "traffic": traffic_of(ef_kernel),
                      "peak_source": peak_src,
                      "ms_per_launch": ef_ms, "algorithmic_gflop_per_launch": ef_flops / 1e9,
-                     "note": "fp32 FMA kernel (1e-4 logit tolerance rules out 1-pass TF32/BF16); vs fp32 SIMT peak "
-                             "148 SM x 128 FMA x %.0f MHz = %.1f TFLOP/s the fraction is %.3f" % (sm_mhz, fp32_peak_tf, ef_tflops / fp32_peak_tf)},
+                     "note": ef_note},
         "roofline_hbm_kernel": {"kernel": "edge_msg_kernel<%d>" % wl["e"], "bound": "hbm", "achieved": msg_bytes / (msg_ms * 1e-3) / 1e9,
                                 "peak": hbm, "unit": "GB/s", "frac": msg_bytes / (msg_ms * 1e-3) / 1e9 / hbm,
                                 "traffic": traffic_of("edge_msg_kernel<%d>" % wl["e"]), "algorithmic_bytes_per_launch": msg_bytes,
@@ -580,9 +591,10 @@ def main():
         "e2e": {"value": B * world / (ms_e2e / 1000.0), "unit": "graphs/s", "h2d_bytes_per_step": io["h2d"], "d2h_bytes_per_step": io["d2h"],
                 "ms_per_step": ms_e2e, "api": "gnn_motion_planning_b200.batch.HotPath.submit/wait (double-buffered; read-back of "
                                               "step k overlaps the kernels of step k+1)"},
-        "gpu_launches": K * (5 + 3 + 1 + 1 + 1 + 1 + 6 + 5 + 1 + 1 + 1),
+        "gpu_launches": K * (5 + 3 + 1 + 1 + 1 + (3 if wl["e"] == 32 else 1) + 6 + 5 + 1 + 1 + 1),
         "gpu_launches_note": "per step: knn 5 (select,row_count,row_scan,graph_scan,emit) + csr 3 + goal_index + obstacle + node_pre + "
-                             "edge_feature + node_loop x6 + edge_msg x5 + policy + {maze,arm}_edge_graph + result_rows; memsets/copies not counted",
+                             "edge_feature (e=32: obs_table_tc + unit_meta + edge_feature_tc) + node_loop x6 + edge_msg x5 + policy + "
+                             "{maze,arm}_edge_graph + result_rows; memsets/copies not counted",
         "clocks": clocks,
     }
     if world == 1 and not args.no_cpu_baseline:

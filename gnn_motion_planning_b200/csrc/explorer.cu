@@ -1104,6 +1104,7 @@ int explorer_build_image(ExplorerModel& m) {
   }
   // ---- tensor-core image of the edge-feature stage (e = 32): hi / lo TF32 planes in the order of TcCfg<C>
   w.tc_img = -1;
+  w.tc_l02 = -1;
   if (e == 32) {
     const int k0 = (2 * c + 7) / 8 * 8, k4 = (2 * c + 3) / 4 * 4;
     w.tc_img = pk.begin();
@@ -1171,6 +1172,9 @@ int explorer_build_image(ExplorerModel& m) {
     }
     pk.put(T("policy.0.bias"));
     pk.put(pb);
+    w.tc_l02 = pk.begin();
+    put_planes(pk, window(T("process.lin_0.2.weight"), e, 0, e, 0, e), e, e, e);
+    pk.put(T("process.lin_0.2.bias"));
   }
   pk.begin();
   for (int q = 0; q < 4 * e + 64; ++q) pk.buf.push_back(0.f);  // slack: stages may over-read up to a few vectors
@@ -1307,6 +1311,7 @@ int run_forward(gmp_handle* h, int64_t B, const float* v, const int64_t* edge_in
     GMP_CUDA(cudaFuncSetAttribute(policy_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
     if constexpr (E == 32)
       GMP_CUDA(cudaFuncSetAttribute(edge_feature_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<C>::kSmemBytes));
+    GMP_CUDA(cudaFuncSetAttribute(edge_msg_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MsgTc::kBytes));
     attr_done = true;
   }
   const float* W = m.d_weights;
@@ -1395,7 +1400,14 @@ int run_forward(gmp_handle* h, int64_t B, const float* v, const int64_t* edge_in
       GMP_LAUNCH_CHECK();
       tl.end(st);
     }
-    if (it < loop && slot_tiles > 0) {
+    if (it < loop && slot_tiles > 0 && use_tc) {
+      tl.begin(kPhEdgeMsg, st);
+      const int tiles128 = (int)((Et + MsgTc::R - 1) / MsgTc::R);
+      edge_msg_tc_kernel<<<std::min(tiles128, kNumSMs * 4), 128, MsgTc::kBytes, st>>>(W + m.w.tc_l02, (int)Et, ws.csr_src, ws.csr_dst, ws.A,
+                                                                                 ws.B, ws.P, ws.AGG);
+      GMP_LAUNCH_CHECK();
+      tl.end(st);
+    } else if (it < loop && slot_tiles > 0) {
       tl.begin(kPhEdgeMsg, st);
       edge_msg_kernel<E><<<std::min(slot_tiles, msg_grid), kRtThreads, MsgSmem<E>::kBytes, st>>>(m.w, W, (int)Et, ws.csr_src, ws.csr_dst, ws.A, ws.B,
                                                                                                 ws.P, ws.AGG);

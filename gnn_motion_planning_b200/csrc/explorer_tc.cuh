@@ -632,4 +632,164 @@ __global__ void __launch_bounds__(384, 1) edge_feature_tc_kernel(
   if (warp_u == 8) umma::tmem_dealloc(tm, 512);
 }
 
+// ------------------------------------------------------------------------------------------------
+// messages + max aggregation for one round on the tensor cores, e = 32            (model.py:33,38-41)
+// ------------------------------------------------------------------------------------------------
+// Same contract and the same memory pipeline as edge_msg_kernel (explorer.cu): persistent CTAs, the loop-invariant edge
+// term P streamed one tile ahead by TMA bulk copies, A[src] / B[dst] rows gathered from L2 with 8 lanes per row, segmented
+// max with one RED.MAX per (segment, feature).  Only the per-edge 32x32 product m = lin_0[2](hidden) moves: the hidden rows
+// go to TMEM as TF32 hi / lo planes (thread == row), one elected lane issues the 12 tcgen05.mma of the 3xTF32 product and the
+// result comes back with tcgen05.ld.  Tiles are 128 rows (one MMA); each CTA owns 128 TMEM columns, four CTAs per SM.
+struct MsgTc {
+  static constexpr int E = 32, R = 128, RP = R + 1;
+  static constexpr int kPS = R * E;              // staged P tile (row-major)
+  static constexpr int kX = E * RP;              // hidden / message tile, feature-major
+  static constexpr int kW = 2 * E * E + E;       // lin_0[2]: hi plane | lo plane | bias
+  static constexpr size_t kNeed = (size_t)(kPS + kX + kW) * sizeof(float) + 2 * R * sizeof(int);
+  // exactly four CTAs per SM: more would fit in shared memory, but a fifth could not allocate tensor memory
+  static constexpr size_t kBytes = kNeed > 47 * 1024 ? kNeed : 47 * 1024;
+  static constexpr int cXH = 0, cXL = 32, cD = 64;
+};
+
+__global__ void __launch_bounds__(128, 4) edge_msg_tc_kernel(const float* __restrict__ w_l02 /* planes + bias */, int n_slots,
+                                                             const int32_t* __restrict__ csr_src, const int32_t* __restrict__ csr_dst,
+                                                             const float* __restrict__ A, const float* __restrict__ B,
+                                                             const float* __restrict__ P, float* __restrict__ AGG) {
+  using M = MsgTc;
+  constexpr int E = M::E, R = M::R, RP = M::RP;
+  constexpr int LPR = E / 4, RPP = 128 / LPR;
+  extern __shared__ __align__(128) float smem_msg[];
+  float* PS = smem_msg;                       // first: 128 B aligned for the bulk copy
+  float* X = PS + M::kPS;
+  float* WB = X + M::kX;
+  int* IDX = reinterpret_cast<int*>(WB + M::kW);
+  int* SRC = IDX + R;
+  __shared__ uint64_t bar_p, bar_mma;
+  __shared__ uint32_t tmem_slot;
+  const int warp_u = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int n_tiles = (n_slots + R - 1) / R;
+  int tile = blockIdx.x;
+  auto tile_bytes = [&](int t) { return (uint32_t)(min(R, n_slots - t * R) * E * (int)sizeof(float)); };
+  if (threadIdx.x == 0) {
+    mbar_init(&bar_p, 1);
+    mbar_init(&bar_mma, 1);
+    if (tile < n_tiles) {
+      mbar_expect_tx(&bar_p, tile_bytes(tile));
+      tma_bulk_g2s(PS, P + (size_t)tile * R * E, tile_bytes(tile), &bar_p);
+    }
+  }
+  if (warp_u == 0) umma::tmem_alloc(&tmem_slot, 128);
+  for (int i = threadIdx.x; i < M::kW / 4; i += 128) reinterpret_cast<float4*>(WB)[i] = __ldg(reinterpret_cast<const float4*>(w_l02) + i);
+  umma::fence_proxy_async();
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tm = tmem_slot;
+  const uint32_t tm_u = __shfl_sync(0xffffffffu, tm, 0);
+  const uint32_t trow = tm + ((uint32_t)(warp_u * 32) << 16);
+  const uint32_t wh = umma::desc_lo32(smem_u32(WB), E), wl = umma::desc_lo32(smem_u32(WB + E * E), E);
+  const float* bias = WB + 2 * E * E;
+  uint32_t ph_p = 0, ph_m = 0;
+  const int q = threadIdx.x % LPR, rsub = threadIdx.x / LPR;
+  int nsrc, ndst;
+  auto load_indices = [&](int t) {
+    const int slot = t * R + threadIdx.x;
+    const bool ok = t < n_tiles && slot < n_slots;
+    nsrc = ok ? __ldg(csr_src + slot) : -1;
+    ndst = ok ? __ldg(csr_dst + slot) : -1;
+  };
+  load_indices(tile);
+  for (; tile < n_tiles; tile += gridDim.x) {
+    SRC[threadIdx.x] = nsrc;
+    IDX[threadIdx.x] = ndst;
+    __syncthreads();           // indices visible; X free (previous scan done)
+    load_indices(tile + gridDim.x);
+    mbar_wait(&bar_p, ph_p);   // this tile's P block has landed
+    ph_p ^= 1;
+    constexpr int UB = 8;      // 8 rows per thread in flight: all 16 row gathers are issued before the first is consumed
+#pragma unroll
+    for (int base = 0; base < R; base += UB * RPP) {
+      float4 av[UB], bv[UB];
+      int sv[UB];
+#pragma unroll
+      for (int u = 0; u < UB; ++u) {
+        const int r = base + rsub + u * RPP;
+        const int s = SRC[r], d = IDX[r];
+        sv[u] = s;
+        av[u] = __ldg(reinterpret_cast<const float4*>(A + (size_t)max(s, 0) * E) + q);
+        bv[u] = __ldg(reinterpret_cast<const float4*>(B + (size_t)max(d, 0) * E) + q);
+      }
+#pragma unroll
+      for (int u = 0; u < UB; ++u) {
+        const int r = base + rsub + u * RPP;
+        const float4 p = *reinterpret_cast<const float4*>(PS + r * E + 4 * q);
+        const bool ok = sv[u] >= 0;
+        float* x = X + (4 * q) * RP + r;
+        x[0] = ok ? fmaxf(av[u].x + bv[u].x + p.x, 0.0f) : 0.0f;
+        x[RP] = ok ? fmaxf(av[u].y + bv[u].y + p.y, 0.0f) : 0.0f;
+        x[2 * RP] = ok ? fmaxf(av[u].z + bv[u].z + p.z, 0.0f) : 0.0f;
+        x[3 * RP] = ok ? fmaxf(av[u].w + bv[u].w + p.w, 0.0f) : 0.0f;
+      }
+    }
+    __syncthreads();           // X complete; staging buffer consumed
+    const int next = tile + gridDim.x;
+    if (threadIdx.x == 0 && next < n_tiles) {
+      mbar_expect_tx(&bar_p, tile_bytes(next));
+      tma_bulk_g2s(PS, P + (size_t)next * R * E, tile_bytes(next), &bar_p);
+    }
+    {
+      // this thread's hidden row -> TF32 hi / lo planes in TMEM (the A operand)
+      float h[E];
+#pragma unroll
+      for (int k = 0; k < E; ++k) h[k] = X[k * RP + threadIdx.x];
+      umma::st_split<E>(trow + M::cXH, trow + M::cXL, h);
+      umma::wait_st();
+    }
+    umma::fence_before_sync();
+    __syncthreads();           // every row published (and every thread has read its row of X)
+    if (warp_u == 0) {
+      umma::fence_after_sync();
+      if (umma::elect_one()) {
+        umma::gemm3_fixed<E, E, E>(tm_u + M::cD, tm_u + M::cXH, tm_u + M::cXL, wh, wl, false);
+        umma::commit(&bar_mma);
+      }
+      __syncwarp();
+    }
+    umma::mbar_wait_guard(&bar_mma, ph_m);
+    ph_m ^= 1;
+    umma::fence_after_sync();
+    {
+      float mrow[E];
+      umma::ld32(trow + M::cD, mrow);
+      umma::wait_ld();
+#pragma unroll
+      for (int n = 0; n < E; ++n) X[n * RP + threadIdx.x] = mrow[n] + bias[n];
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    // segmented max: thread = (feature n, row group); rows of a group are walked in CSR order, so a
+    // target's rows are consecutive; one RED per (segment, feature), 128 B coalesced across the warp.
+    constexpr int GROUPS = 128 / E;
+    constexpr int ROWS = R / GROUPS;
+    const int n = threadIdx.x % E;
+    const int r0 = (threadIdx.x / E) * ROWS;
+    int cur = IDX[r0];
+    float run = -INFINITY;
+    for (int i = 0; i < ROWS; ++i) {
+      const int d = IDX[r0 + i];
+      if (d != cur) {
+        if (cur >= 0) atomic_max_f32(AGG + (size_t)cur * E + n, run);
+        cur = d;
+        run = -INFINITY;
+      }
+      run = fmaxf(run, X[n * RP + r0 + i]);
+    }
+    if (cur >= 0) atomic_max_f32(AGG + (size_t)cur * E + n, run);
+    // (the loop-top barrier protects IDX / X; tensor memory is rewritten only after the next tile's barriers)
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp_u == 0) umma::tmem_dealloc(tm, 128);
+}
+
 }  // namespace gmp

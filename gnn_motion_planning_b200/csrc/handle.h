@@ -40,6 +40,7 @@ struct ExplorerW {
   int p2;                            // policy.2: [Wt | b | policy.4 weight [E]]
   int goal_enc;                      // [E]
   int tc_img;                        // tensor-core image of the edge-feature stage (explorer_tc.cuh), -1 if none
+  int tc_l02;                        // lin_0.2 for the tensor-core message kernel: [hi plane | lo plane | bias], -1 if none
 };
 
 struct ExplorerModel {

@@ -1105,6 +1105,7 @@ int explorer_build_image(ExplorerModel& m) {
   // ---- tensor-core image of the edge-feature stage (e = 32): hi / lo TF32 planes in the order of TcCfg<C>
   w.tc_img = -1;
   w.tc_l02 = -1;
+  w.tc_p2 = -1;
   if (e == 32) {
     const int k0 = (2 * c + 7) / 8 * 8, k4 = (2 * c + 3) / 4 * 4;
     w.tc_img = pk.begin();
@@ -1175,6 +1176,11 @@ int explorer_build_image(ExplorerModel& m) {
     w.tc_l02 = pk.begin();
     put_planes(pk, window(T("process.lin_0.2.weight"), e, 0, e, 0, e), e, e, e);
     pk.put(T("process.lin_0.2.bias"));
+    pk.put(std::vector<float>(e, 0.f));
+    w.tc_p2 = pk.begin();
+    put_planes(pk, window(T("policy.2.weight"), e, 0, e, 0, e), e, e, e);
+    pk.put(T("policy.2.bias"));
+    pk.put(T("policy.4.weight"));
   }
   pk.begin();
   for (int q = 0; q < 4 * e + 64; ++q) pk.buf.push_back(0.f);  // slack: stages may over-read up to a few vectors
@@ -1311,7 +1317,8 @@ int run_forward(gmp_handle* h, int64_t B, const float* v, const int64_t* edge_in
     GMP_CUDA(cudaFuncSetAttribute(policy_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
     if constexpr (E == 32)
       GMP_CUDA(cudaFuncSetAttribute(edge_feature_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<C>::kSmemBytes));
-    GMP_CUDA(cudaFuncSetAttribute(edge_msg_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MsgTc::kBytes));
+    GMP_CUDA(cudaFuncSetAttribute(edge_msg_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MsgTc::kBytes));
+    GMP_CUDA(cudaFuncSetAttribute(edge_msg_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MsgTc::kBytes));
     attr_done = true;
   }
   const float* W = m.d_weights;
@@ -1403,8 +1410,8 @@ int run_forward(gmp_handle* h, int64_t B, const float* v, const int64_t* edge_in
     if (it < loop && slot_tiles > 0 && use_tc) {
       tl.begin(kPhEdgeMsg, st);
       const int tiles128 = (int)((Et + MsgTc::R - 1) / MsgTc::R);
-      edge_msg_tc_kernel<<<std::min(tiles128, kNumSMs * 4), 128, MsgTc::kBytes, st>>>(W + m.w.tc_l02, (int)Et, ws.csr_src, ws.csr_dst, ws.A,
-                                                                                 ws.B, ws.P, ws.AGG);
+      edge_msg_tc_kernel<false><<<std::min(tiles128, kNumSMs * 4), 128, MsgTc::kBytes, st>>>(W + m.w.tc_l02, (int)Et, ws.csr_src, ws.csr_dst,
+                                                                                        ws.A, ws.B, ws.P, ws.AGG, PolicyOut{});
       GMP_LAUNCH_CHECK();
       tl.end(st);
     } else if (it < loop && slot_tiles > 0) {
@@ -1417,7 +1424,13 @@ int run_forward(gmp_handle* h, int64_t B, const float* v, const int64_t* edge_in
   }
   tl.begin(kPhPolicy, st);
   if (dense && dense_off[B] > 0) GMP_CUDA(cudaMemsetAsync(dense, 0, dense_off[B] * sizeof(float), st));
-  if (slot_tiles > 0) {
+  if (slot_tiles > 0 && use_tc) {
+    const int tiles128 = (int)((Et + MsgTc::R - 1) / MsgTc::R);
+    edge_msg_tc_kernel<true><<<std::min(tiles128, kNumSMs * 4), 128, MsgTc::kBytes, st>>>(
+        W + m.w.tc_p2, (int)Et, ws.csr_src, ws.csr_dst, ws.A, ws.B, ws.Q, nullptr,
+        PolicyOut{ws.csr_eid, ws.edge_ptr, ws.node_ptr, ws.dense_off, (int)B, logits, dense});
+    GMP_LAUNCH_CHECK();
+  } else if (slot_tiles > 0) {
     policy_kernel<E><<<slot_tiles, kRtThreads, smem1, st>>>(m.w, W, (int)Et, ws.csr_src, ws.csr_dst, ws.csr_eid, ws.A, ws.B, ws.Q,
                                                           ws.edge_ptr, ws.node_ptr, ws.dense_off, (int)B, logits, dense);
     GMP_LAUNCH_CHECK();

@@ -644,17 +644,27 @@ struct MsgTc {
   static constexpr int E = 32, R = 128, RP = R + 1;
   static constexpr int kPS = R * E;              // staged P tile (row-major)
   static constexpr int kX = E * RP;              // hidden / message tile, feature-major
-  static constexpr int kW = 2 * E * E + E;       // lin_0[2]: hi plane | lo plane | bias
+  static constexpr int kW = 2 * E * E + 2 * E;   // lin_0[2] / policy[2]: hi plane | lo plane | bias | (policy[4] weight)
   static constexpr size_t kNeed = (size_t)(kPS + kX + kW) * sizeof(float) + 2 * R * sizeof(int);
   // exactly four CTAs per SM: more would fit in shared memory, but a fifth could not allocate tensor memory
   static constexpr size_t kBytes = kNeed > 47 * 1024 ? kNeed : 47 * 1024;
   static constexpr int cXH = 0, cXL = 32, cD = 64;
 };
 
+// POLICY = false: messages, AGG = segmented max of lin_0[2](hidden)                              (model.py:33,38-41)
+// POLICY = true : policy head, logit = policy[4](relu(policy[2](hidden))) with hidden = relu(G[src] + H[dst] + Q), written
+//                 at the edge's COO position (and into the dense [N, N] matrix)               (model.py:145-150);
+//                 the weight image is then [hi plane | lo plane | bias | policy.4 weight]
+struct PolicyOut {
+  const int32_t* csr_eid; const int32_t* edge_ptr; const int32_t* node_ptr; const int64_t* dense_off; int n_graphs;
+  float* logits; float* dense;
+};
+
+template <bool POLICY>
 __global__ void __launch_bounds__(128, 4) edge_msg_tc_kernel(const float* __restrict__ w_l02 /* planes + bias */, int n_slots,
                                                              const int32_t* __restrict__ csr_src, const int32_t* __restrict__ csr_dst,
                                                              const float* __restrict__ A, const float* __restrict__ B,
-                                                             const float* __restrict__ P, float* __restrict__ AGG) {
+                                                             const float* __restrict__ P, float* __restrict__ AGG, PolicyOut po) {
   using M = MsgTc;
   constexpr int E = M::E, R = M::R, RP = M::RP;
   constexpr int LPR = E / 4, RPP = 128 / LPR;
@@ -758,6 +768,34 @@ __global__ void __launch_bounds__(128, 4) edge_msg_tc_kernel(const float* __rest
     umma::mbar_wait_guard(&bar_mma, ph_m);
     ph_m ^= 1;
     umma::fence_after_sync();
+    if constexpr (POLICY) {
+      float mrow[E];
+      umma::ld32(trow + M::cD, mrow);
+      umma::wait_ld();
+      const float* w4 = bias + E;
+      float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+#pragma unroll
+      for (int n = 0; n < E; n += 4) {
+        l0 = fmaf(fmaxf(mrow[n] + bias[n], 0.f), w4[n], l0);
+        l1 = fmaf(fmaxf(mrow[n + 1] + bias[n + 1], 0.f), w4[n + 1], l1);
+        l2 = fmaf(fmaxf(mrow[n + 2] + bias[n + 2], 0.f), w4[n + 2], l2);
+        l3 = fmaf(fmaxf(mrow[n + 3] + bias[n + 3], 0.f), w4[n + 3], l3);
+      }
+      const float logit = (l0 + l1) + (l2 + l3);
+      const int slot = tile * R + threadIdx.x;
+      if (slot < n_slots) {
+        po.logits[po.csr_eid[slot]] = logit;
+        if (po.dense) {
+          const int g = find_segment(po.edge_ptr, po.n_graphs, slot);
+          const int n0 = po.node_ptr[g];
+          const int64_t ng = po.node_ptr[g + 1] - n0;
+          const int sn = SRC[threadIdx.x] - n0, dn = IDX[threadIdx.x] - n0;
+          po.dense[po.dense_off[g] + (int64_t)dn * ng + sn] = logit;   // out[dst, src]   (model.py:149)
+        }
+      }
+      umma::fence_before_sync();
+      continue;   // (the loop-top barrier orders this tile's tensor-memory reads before the next tile's writes)
+    }
     {
       float mrow[E];
       umma::ld32(trow + M::cD, mrow);

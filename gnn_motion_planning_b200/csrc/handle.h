@@ -40,7 +40,8 @@ struct ExplorerW {
   int p2;                            // policy.2: [Wt | b | policy.4 weight [E]]
   int goal_enc;                      // [E]
   int tc_img;                        // tensor-core image of the edge-feature stage (explorer_tc.cuh), -1 if none
-  int tc_l02;                        // lin_0.2 for the tensor-core message kernel: [hi plane | lo plane | bias], -1 if none
+  int tc_l02;                        // lin_0.2 for the tensor-core message kernel: [hi plane | lo plane | bias | pad], -1 if none
+  int tc_p2;                         // policy.2 for the tensor-core policy kernel: [hi plane | lo plane | bias | policy.4 weight]
 };
 
 struct ExplorerModel {

@@ -1173,15 +1173,16 @@ int explorer_build_image(ExplorerModel& m) {
     }
     pk.put(T("policy.0.bias"));
     pk.put(pb);
-    w.tc_l02 = pk.begin();
-    put_planes(pk, window(T("process.lin_0.2.weight"), e, 0, e, 0, e), e, e, e);
-    pk.put(T("process.lin_0.2.bias"));
-    pk.put(std::vector<float>(e, 0.f));
-    w.tc_p2 = pk.begin();
-    put_planes(pk, window(T("policy.2.weight"), e, 0, e, 0, e), e, e, e);
-    pk.put(T("policy.2.bias"));
-    pk.put(T("policy.4.weight"));
   }
+  // tensor-core message / policy kernels (e = 32 and 64): [hi plane | lo plane | bias | policy.4 weight or padding]
+  w.tc_l02 = pk.begin();
+  put_planes(pk, window(T("process.lin_0.2.weight"), e, 0, e, 0, e), e, e, e);
+  pk.put(T("process.lin_0.2.bias"));
+  pk.put(std::vector<float>(e, 0.f));
+  w.tc_p2 = pk.begin();
+  put_planes(pk, window(T("policy.2.weight"), e, 0, e, 0, e), e, e, e);
+  pk.put(T("policy.2.bias"));
+  pk.put(T("policy.4.weight"));
   pk.begin();
   for (int q = 0; q < 4 * e + 64; ++q) pk.buf.push_back(0.f);  // slack: stages may over-read up to a few vectors
   if (m.d_weights) cudaFree(m.d_weights);
@@ -1281,7 +1282,8 @@ int run_forward(gmp_handle* h, int64_t B, const float* v, const int64_t* edge_in
   }
   const int64_t obs_tiles = obs_tile_ptr[B];
   // tensor-core edge-feature stage (e = 32): obstacle-table units of tc_per() rows per chunk
-  const bool use_tc = E == 32 && m.w.tc_img >= 0 && m.edge_feature_mode != 0;
+  const bool use_tc = E == 32 && m.w.tc_img >= 0 && m.edge_feature_mode != 0;   // tensor-core edge-feature stage
+  const bool use_tc_msg = m.w.tc_l02 >= 0 && m.edge_feature_mode != 0;         // tensor-core message / policy kernels
   std::vector<int64_t> tc_off(B + 1, 0);
   if (use_tc)
     for (int64_t g = 0; g < B; ++g) {
@@ -1317,8 +1319,8 @@ int run_forward(gmp_handle* h, int64_t B, const float* v, const int64_t* edge_in
     GMP_CUDA(cudaFuncSetAttribute(policy_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
     if constexpr (E == 32)
       GMP_CUDA(cudaFuncSetAttribute(edge_feature_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<C>::kSmemBytes));
-    GMP_CUDA(cudaFuncSetAttribute(edge_msg_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MsgTc::kBytes));
-    GMP_CUDA(cudaFuncSetAttribute(edge_msg_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MsgTc::kBytes));
+    GMP_CUDA(cudaFuncSetAttribute(edge_msg_tc_kernel<E, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MsgTc<E>::kBytes));
+    GMP_CUDA(cudaFuncSetAttribute(edge_msg_tc_kernel<E, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MsgTc<E>::kBytes));
     attr_done = true;
   }
   const float* W = m.d_weights;
@@ -1407,10 +1409,10 @@ int run_forward(gmp_handle* h, int64_t B, const float* v, const int64_t* edge_in
       GMP_LAUNCH_CHECK();
       tl.end(st);
     }
-    if (it < loop && slot_tiles > 0 && use_tc) {
+    if (it < loop && slot_tiles > 0 && use_tc_msg) {
       tl.begin(kPhEdgeMsg, st);
-      const int tiles128 = (int)((Et + MsgTc::R - 1) / MsgTc::R);
-      edge_msg_tc_kernel<false><<<std::min(tiles128, kNumSMs * 4), 128, MsgTc::kBytes, st>>>(W + m.w.tc_l02, (int)Et, ws.csr_src, ws.csr_dst,
+      const int tiles128 = (int)((Et + MsgTc<E>::R - 1) / MsgTc<E>::R);
+      edge_msg_tc_kernel<E, false><<<std::min(tiles128, kNumSMs * MsgTc<E>::kCtas), 128, MsgTc<E>::kBytes, st>>>(W + m.w.tc_l02, (int)Et, ws.csr_src, ws.csr_dst,
                                                                                         ws.A, ws.B, ws.P, ws.AGG, PolicyOut{});
       GMP_LAUNCH_CHECK();
       tl.end(st);
@@ -1424,9 +1426,9 @@ int run_forward(gmp_handle* h, int64_t B, const float* v, const int64_t* edge_in
   }
   tl.begin(kPhPolicy, st);
   if (dense && dense_off[B] > 0) GMP_CUDA(cudaMemsetAsync(dense, 0, dense_off[B] * sizeof(float), st));
-  if (slot_tiles > 0 && use_tc) {
-    const int tiles128 = (int)((Et + MsgTc::R - 1) / MsgTc::R);
-    edge_msg_tc_kernel<true><<<std::min(tiles128, kNumSMs * 4), 128, MsgTc::kBytes, st>>>(
+  if (slot_tiles > 0 && use_tc_msg) {
+    const int tiles128 = (int)((Et + MsgTc<E>::R - 1) / MsgTc<E>::R);
+    edge_msg_tc_kernel<E, true><<<std::min(tiles128, kNumSMs * MsgTc<E>::kCtas), 128, MsgTc<E>::kBytes, st>>>(
         W + m.w.tc_p2, (int)Et, ws.csr_src, ws.csr_dst, ws.A, ws.B, ws.Q, nullptr,
         PolicyOut{ws.csr_eid, ws.edge_ptr, ws.node_ptr, ws.dense_off, (int)B, logits, dense});
     GMP_LAUNCH_CHECK();

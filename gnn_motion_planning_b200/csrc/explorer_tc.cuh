@@ -640,15 +640,21 @@ __global__ void __launch_bounds__(384, 1) edge_feature_tc_kernel(
 // max with one RED.MAX per (segment, feature).  Only the per-edge 32x32 product m = lin_0[2](hidden) moves: the hidden rows
 // go to TMEM as TF32 hi / lo planes (thread == row), one elected lane issues the 12 tcgen05.mma of the 3xTF32 product and the
 // result comes back with tcgen05.ld.  Tiles are 128 rows (one MMA); each CTA owns 128 TMEM columns, four CTAs per SM.
+template <int E_>
 struct MsgTc {
-  static constexpr int E = 32, R = 128, RP = R + 1;
+  static constexpr int E = E_, R = 128, RP = R + 1;
   static constexpr int kPS = R * E;              // staged P tile (row-major)
   static constexpr int kX = E * RP;              // hidden / message tile, feature-major
   static constexpr int kW = 2 * E * E + 2 * E;   // lin_0[2] / policy[2]: hi plane | lo plane | bias | (policy[4] weight)
   static constexpr size_t kNeed = (size_t)(kPS + kX + kW) * sizeof(float) + 2 * R * sizeof(int);
-  // exactly four CTAs per SM: more would fit in shared memory, but a fifth could not allocate tensor memory
-  static constexpr size_t kBytes = kNeed > 47 * 1024 ? kNeed : 47 * 1024;
-  static constexpr int cXH = 0, cXL = 32, cD = 64;
+  // tensor memory: XH | XL | D = 3E columns, allocated as a power of two; kCtas CTAs per SM share the 512 columns.  The
+  // shared-memory request is padded so that exactly kCtas fit: one more could not allocate tensor memory and would stall
+  static constexpr int kTmemCols = E == 32 ? 128 : 256;
+  static constexpr int kCtas = 512 / kTmemCols;
+  static constexpr size_t kPad = (size_t)(227 * 1024) / (kCtas + 1) + 1024;
+  static constexpr size_t kBytes = kNeed > kPad ? kNeed : kPad;
+  static_assert(kBytes * kCtas <= 227 * 1024, "kCtas CTAs must fit in shared memory");
+  static constexpr int cXH = 0, cXL = E, cD = 2 * E;
 };
 
 // POLICY = false: messages, AGG = segmented max of lin_0[2](hidden)                              (model.py:33,38-41)
@@ -660,12 +666,12 @@ struct PolicyOut {
   float* logits; float* dense;
 };
 
-template <bool POLICY>
-__global__ void __launch_bounds__(128, 4) edge_msg_tc_kernel(const float* __restrict__ w_l02 /* planes + bias */, int n_slots,
+template <int E_, bool POLICY>
+__global__ void __launch_bounds__(128, MsgTc<E_>::kCtas) edge_msg_tc_kernel(const float* __restrict__ w_l02 /* planes + bias */, int n_slots,
                                                              const int32_t* __restrict__ csr_src, const int32_t* __restrict__ csr_dst,
                                                              const float* __restrict__ A, const float* __restrict__ B,
                                                              const float* __restrict__ P, float* __restrict__ AGG, PolicyOut po) {
-  using M = MsgTc;
+  using M = MsgTc<E_>;
   constexpr int E = M::E, R = M::R, RP = M::RP;
   constexpr int LPR = E / 4, RPP = 128 / LPR;
   extern __shared__ __align__(128) float smem_msg[];
@@ -688,7 +694,7 @@ __global__ void __launch_bounds__(128, 4) edge_msg_tc_kernel(const float* __rest
       tma_bulk_g2s(PS, P + (size_t)tile * R * E, tile_bytes(tile), &bar_p);
     }
   }
-  if (warp_u == 0) umma::tmem_alloc(&tmem_slot, 128);
+  if (warp_u == 0) umma::tmem_alloc(&tmem_slot, M::kTmemCols);
   for (int i = threadIdx.x; i < M::kW / 4; i += 128) reinterpret_cast<float4*>(WB)[i] = __ldg(reinterpret_cast<const float4*>(w_l02) + i);
   umma::fence_proxy_async();
   umma::fence_before_sync();
@@ -770,7 +776,7 @@ __global__ void __launch_bounds__(128, 4) edge_msg_tc_kernel(const float* __rest
     umma::fence_after_sync();
     if constexpr (POLICY) {
       float mrow[E];
-      umma::ld32(trow + M::cD, mrow);
+      tc_detail::ld_cols<E>(trow + M::cD, mrow);
       umma::wait_ld();
       const float* w4 = bias + E;
       float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
@@ -798,7 +804,7 @@ __global__ void __launch_bounds__(128, 4) edge_msg_tc_kernel(const float* __rest
     }
     {
       float mrow[E];
-      umma::ld32(trow + M::cD, mrow);
+      tc_detail::ld_cols<E>(trow + M::cD, mrow);
       umma::wait_ld();
 #pragma unroll
       for (int n = 0; n < E; ++n) X[n * RP + threadIdx.x] = mrow[n] + bias[n];
@@ -827,7 +833,7 @@ __global__ void __launch_bounds__(128, 4) edge_msg_tc_kernel(const float* __rest
   }
   umma::fence_before_sync();
   __syncthreads();
-  if (warp_u == 0) umma::tmem_dealloc(tm, 128);
+  if (warp_u == 0) umma::tmem_dealloc(tm, M::kTmemCols);
 }
 
 }  // namespace gmp

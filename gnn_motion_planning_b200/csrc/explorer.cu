@@ -1241,16 +1241,6 @@ int64_t carve_explorer(Carver& cv, ExWs& ws, int e, int64_t B, int64_t Nt, int64
   return cv.bytes();
 }
 
-// head start (SM cycles) of tile 0 over tile 1 in the tensor-core edge-feature kernel; GMP_TC_PHASE_DELAY overrides (tuning)
-int tc_phase_delay() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = std::getenv("GMP_TC_PHASE_DELAY");
-    v = e ? std::atoi(e) : 0;
-  }
-  return v;
-}
-
 template <int C, int E, int S>
 int run_forward(gmp_handle* h, int64_t B, const float* v, const int64_t* edge_index, int64_t row_stride, const float* goal,
                 const float* obstacles, const int32_t* node_ptr_h, const int32_t* edge_ptr_h, const int32_t* obs_ptr_h, int loop,
@@ -1381,8 +1371,7 @@ int run_forward(gmp_handle* h, int64_t B, const float* v, const int64_t* edge_in
                                                                           ws.tc_tab_off, ws.tc_unit_meta);
       GMP_LAUNCH_CHECK();
       edge_feature_tc_kernel<C><<<std::min<int>(tile_e[B], kNumSMs), 384, TcCfg<C>::kSmemBytes, st>>>(
-          W + m.w.tc_img, v, ws.csr_src, ws.csr_dst, ws.tc_unit_meta, tile_e[B], ws.tc_tables, tc_stride, use_obstacles, tc_phase_delay(),
-          ws.P, ws.Q);
+          W + m.w.tc_img, v, ws.csr_src, ws.csr_dst, ws.tc_unit_meta, tile_e[B], ws.tc_tables, tc_stride, use_obstacles, ws.P, ws.Q);
       GMP_LAUNCH_CHECK();
       tc_done = true;
     }

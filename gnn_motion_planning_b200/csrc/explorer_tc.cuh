@@ -14,9 +14,10 @@
 //     LayerNorm, TF32 split, tcgen05.st) overlaps the other tile's MMAs;
 //   * activations never touch shared memory: A operands are read from TMEM, accumulators are read back with the
 //     32x32b shape (thread == row) so softmax / LayerNorm / residuals are thread-local exactly as in the SIMT kernels;
-//   * shared memory holds the B operands only: all weights of this stage as hi / lo TF32 planes (resident, ~146 KB)
-//     and ONE obstacle-table buffer (<= 48 KB: scale*Wq^T Wk o and Wv o of <= 96 obstacles, hi / lo) that warp 8
-//     refills with a TMA bulk copy as soon as both tiles' P.V MMAs have retired -- the refill overlaps the FFN stages.
+//   * shared memory holds the B operands only: all weights of this stage as hi / lo TF32 planes (resident, 139-158 KB)
+//     and ONE obstacle-table buffer (<= 64 KB: scale*Wq^T Wk o and Wv o of <= 128 obstacles, hi / lo) that warp 8
+//     refills with a TMA bulk copy once both tiles have published map_feed.w_1's operand (every P.V product of the block
+//     has retired by then) -- the refill overlaps the two FFN stages.
 //
 // TMEM columns of a tile (256 of the CTA's 512): XH [0,32) XL [32,64) A operand; A1 [64,128) accumulators
 // (Gx | Vx, FFN, Q | P); SC [128,224) scores -> probabilities hi (in place); PL [0,96) probabilities lo (overlays the
@@ -156,13 +157,13 @@ template <int C>
 __global__ void __launch_bounds__(384, 1) edge_feature_tc_kernel(
     const float* __restrict__ tcw, const float* __restrict__ v, const int32_t* __restrict__ csr_src,
     const int32_t* __restrict__ csr_dst, const int4* __restrict__ unit_meta, int n_units, const float* __restrict__ tc_tables,
-    int64_t tc_tab_stride, int use_obstacles, int phase_delay, float* __restrict__ P, float* __restrict__ Q) {
+    int64_t tc_tab_stride, int use_obstacles, float* __restrict__ P, float* __restrict__ Q) {
   using Cf = TcCfg<C>;
   constexpr int E = 32, K0 = Cf::K0;
   extern __shared__ __align__(128) float smem_tc[];
   float* img = smem_tc;
   float* tabbuf = smem_tc + Cf::kImage;
-  __shared__ uint64_t bar_ready[2], bar_done[2], bar_tabfull, bar_tabfree;
+  __shared__ uint64_t bar_ready[2], bar_done[2], bar_tabfull;
   __shared__ uint32_t tmem_slot;
 
   const int warp_u = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
@@ -175,7 +176,7 @@ __global__ void __launch_bounds__(384, 1) edge_feature_tc_kernel(
   if (threadIdx.x == 0) {
     mbar_init(&bar_ready[0], 128); mbar_init(&bar_ready[1], 128);
     mbar_init(&bar_done[0], 1); mbar_init(&bar_done[1], 1);
-    mbar_init(&bar_tabfull, 1); mbar_init(&bar_tabfree, 1);
+    mbar_init(&bar_tabfull, 1);
   }
   if (warp_u == 8) umma::tmem_alloc(&tmem_slot, 512);
   umma::fence_proxy_async();
@@ -234,7 +235,7 @@ __global__ void __launch_bounds__(384, 1) edge_feature_tc_kernel(
     };
     cursor_load();
 #ifdef GMP_TC_PROFILE
-    long long prof_ready[2] = {0, 0}, prof_tab = 0, prof_free = 0, prof_t0 = clock64();
+    long long prof_ready[2] = {0, 0}, prof_tab = 0, prof_t0 = clock64();
     long long prof_issue[5] = {0, 0, 0, 0, 0};   // K0-wide encoder layer, 32x32, GV (+scores), P.V, Q|P
 #endif
     // lo words of the weight descriptors: hi / lo plane of the matrix at float offset `off` with `rows` rows and K columns
@@ -353,8 +354,8 @@ __global__ void __launch_bounds__(384, 1) edge_feature_tc_kernel(
     }
 #ifdef GMP_TC_PROFILE
     if (blockIdx.x == 0 && (threadIdx.x & 31) == 0)
-      printf("tc profile: issuer total %lld cyc; waiting ready[0] %lld ready[1] %lld tables %lld (unused %lld); issuing: enc0 %lld 32x32 %lld "
-             "GV+scores %lld PV %lld QP %lld\n", clock64() - prof_t0, prof_ready[0], prof_ready[1], prof_tab, prof_free, prof_issue[0],
+      printf("tc profile: issuer total %lld cyc; waiting ready[0] %lld ready[1] %lld tables %lld; issuing: enc0 %lld 32x32 %lld "
+             "GV+scores %lld PV %lld QP %lld\n", clock64() - prof_t0, prof_ready[0], prof_ready[1], prof_tab, prof_issue[0],
              prof_issue[1], prof_issue[2], prof_issue[3], prof_issue[4]);
 #endif
   } else {
@@ -404,13 +405,6 @@ __global__ void __launch_bounds__(384, 1) edge_feature_tc_kernel(
       }
     };
     prefetch_unit(blockIdx.x);
-    // The issuer serves the tiles alternately, so whatever head start tile 0 has over tile 1 persists for the whole kernel.
-    // Starting tile 1 about half an epilogue late puts the tiles in anti-phase: one tile's tcgen05.ld / st traffic then
-    // overlaps the other tile's ALU work instead of both queueing on the TMEM port at the same time.
-    if (tile == 1 && phase_delay > 0) {
-      const long long t_go = clock64() + phase_delay;
-      while (clock64() < t_go) {}
-    }
     for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
       const int4 meta = meta_nx;
       const int slot = meta.x + tile * 128 + row;

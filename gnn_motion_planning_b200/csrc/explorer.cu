@@ -36,6 +36,7 @@
 #include "handle.h"
 #include "rowtile.cuh"
 #include "explorer_tc.cuh"
+#include "explorer_tc64.cuh"
 
 namespace gmp {
 namespace {
@@ -1174,6 +1175,65 @@ int explorer_build_image(ExplorerModel& m) {
     pk.put(T("policy.0.bias"));
     pk.put(pb);
   }
+  for (int q = 0; q < 5; ++q) w.tc64_img[q] = -1;
+  if (e == 64) {
+    // phase images of the embed-64 tensor-core edge-feature stage (Tc64Cfg<C>)
+    const int k0 = (2 * c + 7) / 8 * 8;
+    std::vector<double> enc0 = window(T("edge_free_code.0.weight"), 2 * c, 0, e, 0, 2 * c);
+    const std::vector<double> ec0 = window(T("edge_code.0.weight"), 2 * c, 0, e, 0, 2 * c);
+    enc0.insert(enc0.end(), ec0.begin(), ec0.end());
+    w.tc64_img[0] = pk.begin();
+    put_planes(pk, enc0, 2 * e, 2 * c, k0);
+    put_planes(pk, window(T("edge_free_code.2.weight"), e, 0, e, 0, e), e, e, e);
+    pk.put(T("edge_free_code.0.bias")); pk.put(T("edge_code.0.bias")); pk.put(T("edge_free_code.2.bias"));
+    for (int i = 0; i < 3; ++i) {
+      const std::string p = "edge_attentions." + std::to_string(i) + ".";
+      const auto& Wq = T(p + "attention.query.weight");
+      const auto& Wk = T(p + "attention.key.weight");
+      const auto& Wv = T(p + "attention.value.weight");
+      std::vector<double> GV((size_t)2 * e * e);
+      for (int a = 0; a < e; ++a)
+        for (int b = 0; b < e; ++b) {
+          double sum = 0;
+          for (int o = 0; o < e; ++o) sum += (double)Wq[(size_t)o * e + a] * (double)Wk[(size_t)o * e + b];
+          GV[(size_t)a * e + b] = scale * sum;
+          GV[(size_t)(e + a) * e + b] = Wv[(size_t)a * e + b];
+        }
+      w.tc64_img[1 + i] = pk.begin();
+      put_planes(pk, GV, 2 * e, e, e);
+      put_planes(pk, window(T(p + "map_feed.w_1.weight"), e, 0, e, 0, e), e, e, e);
+      put_planes(pk, window(T(p + "map_feed.w_2.weight"), e, 0, e, 0, e), e, e, e);
+      pk.put(T(p + "attention.layer_norm.weight")); pk.put(T(p + "attention.layer_norm.bias"));
+      pk.put(T(p + "map_feed.w_1.bias")); pk.put(T(p + "map_feed.w_2.bias"));
+      pk.put(T(p + "map_feed.layer_norm.weight")); pk.put(T(p + "map_feed.layer_norm.bias"));
+    }
+    {
+      const auto& Wp = T("policy.0.weight");
+      const auto& W0 = T("process.lin_0.0.weight");
+      std::vector<double> QP = window(Wp, 3 * e, 0, e, 2 * e, e), Pef = window(W0, 5 * e, 0, e, 3 * e, e);
+      QP.insert(QP.end(), Pef.begin(), Pef.end());
+      const std::vector<double> W5 = window(W0, 5 * e, 0, e, 4 * e, e);
+      const auto& Wec2 = T("edge_code.2.weight");
+      const auto& bec2 = T("edge_code.2.bias");
+      const auto& b0 = T("process.lin_0.0.bias");
+      std::vector<double> W52((size_t)e * e), pb(e);
+      for (int n = 0; n < e; ++n) {
+        double bsum = b0[n];
+        for (int j = 0; j < e; ++j) bsum += W5[(size_t)n * e + j] * (double)bec2[j];
+        pb[n] = bsum;
+        for (int k = 0; k < e; ++k) {
+          double sum = 0;
+          for (int j = 0; j < e; ++j) sum += W5[(size_t)n * e + j] * (double)Wec2[(size_t)j * e + k];
+          W52[(size_t)n * e + k] = sum;
+        }
+      }
+      w.tc64_img[4] = pk.begin();
+      put_planes(pk, QP, 2 * e, e, e);
+      put_planes(pk, W52, e, e, e);
+      put_planes(pk, ec0, e, 2 * c, k0);
+      pk.put(T("edge_code.0.bias")); pk.put(T("policy.0.bias")); pk.put(pb);
+    }
+  }
   // tensor-core message / policy kernels (e = 32 and 64): [hi plane | lo plane | bias | policy.4 weight or padding]
   w.tc_l02 = pk.begin();
   put_planes(pk, window(T("process.lin_0.2.weight"), e, 0, e, 0, e), e, e, e);
@@ -1207,6 +1267,7 @@ struct ExWs {
   int64_t* tc_tab_off;   // tensor-core edge-feature stage: per-graph float offset of its obstacle-table units
   float* tc_tables;      // 3 blocks x tc_rows x 128 floats (hi / lo planes of M and V per 96-obstacle chunk)
   int4* tc_unit_meta;    // per 256-slot unit: first slot, graph's end slot, obstacle count, table offset
+  int32_t* tc_unit_ptr;  // [B+1] first 256-slot unit of every graph
 };
 
 int64_t carve_explorer(Carver& cv, ExWs& ws, int e, int64_t B, int64_t Nt, int64_t Et, int64_t obs_tiles, int64_t tc_rows) {
@@ -1237,7 +1298,8 @@ int64_t carve_explorer(Carver& cv, ExWs& ws, int e, int64_t B, int64_t Nt, int64
   ws.Q = cv.take<float>(Et * e);
   ws.tc_tab_off = cv.take<int64_t>(B + 1);
   ws.tc_tables = cv.take<float>(3 * tc_rows * 4 * e);
-  ws.tc_unit_meta = cv.take<int4>(e == 32 ? Et / 256 + B + 1 : 0);
+  ws.tc_unit_meta = cv.take<int4>(Et / 256 + B + 1);
+  ws.tc_unit_ptr = cv.take<int32_t>(B + 1);
   return cv.bytes();
 }
 
@@ -1274,12 +1336,18 @@ int run_forward(gmp_handle* h, int64_t B, const float* v, const int64_t* edge_in
   // tensor-core edge-feature stage (e = 32): obstacle-table units of tc_per() rows per chunk
   const bool use_tc = E == 32 && m.w.tc_img >= 0 && m.edge_feature_mode != 0;   // tensor-core edge-feature stage
   const bool use_tc_msg = m.w.tc_l02 >= 0 && m.edge_feature_mode != 0;         // tensor-core message / policy kernels
+  // embed 64: the phase-split tensor-core stage (explorer_tc64.cuh) handles graphs with at most 32 obstacles (the arms have <= 12)
+  bool use_tc64 = E == 64 && m.w.tc64_img[0] >= 0 && m.edge_feature_mode != 0;
+  for (int64_t g = 0; g < B && use_tc64; ++g)
+    if (obs_ptr[g + 1] - obs_ptr[g] > 32) use_tc64 = false;
   std::vector<int64_t> tc_off(B + 1, 0);
-  if (use_tc)
+  std::vector<int32_t> unit_ptr(B + 1, 0);
+  if (use_tc || use_tc64)
     for (int64_t g = 0; g < B; ++g) {
       const int no = obs_ptr[g + 1] - obs_ptr[g];
-      const int nch = tc_nchunks(no);
+      const int nch = E == 64 ? (no > 0) : tc_nchunks(no);
       tc_off[g + 1] = tc_off[g] + (int64_t)nch * tc_per(no, nch) * 4 * E;
+      unit_ptr[g + 1] = unit_ptr[g] + (int32_t)(((int64_t)edge_ptr_h[g + 1] - edge_ptr_h[g] + 255) / 256);
     }
   const int64_t tc_rows = tc_off[B] / (4 * E);
   GMP_REQUIRE(tc_off[B] < (int64_t)1 << 31, "too many obstacle rows in one call for the tensor-core table index");
@@ -1294,7 +1362,10 @@ int run_forward(gmp_handle* h, int64_t B, const float* v, const int64_t* edge_in
   GMP_CUDA(cudaMemcpyAsync(ws.tile_ptr_e, tile_e, (B + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   GMP_CUDA(cudaMemcpyAsync(ws.tile_ptr_n, tile_n, (B + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   GMP_CUDA(cudaMemcpyAsync(ws.dense_off, dense_off.data(), (B + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
-  if (use_tc) GMP_CUDA(cudaMemcpyAsync(ws.tc_tab_off, tc_off.data(), (B + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  if (use_tc || use_tc64) {
+    GMP_CUDA(cudaMemcpyAsync(ws.tc_tab_off, tc_off.data(), (B + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    GMP_CUDA(cudaMemcpyAsync(ws.tc_unit_ptr, unit_ptr.data(), (B + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  }
   // (pageable sources: cudaMemcpyAsync has staged them before returning, so the vectors may die)
 
   const size_t smem = Smem<E, true>::kBytes;     // node / obstacle kernels (two activation buffers)
@@ -1309,6 +1380,11 @@ int run_forward(gmp_handle* h, int64_t B, const float* v, const int64_t* edge_in
     GMP_CUDA(cudaFuncSetAttribute(policy_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
     if constexpr (E == 32)
       GMP_CUDA(cudaFuncSetAttribute(edge_feature_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<C>::kSmemBytes));
+    if constexpr (E == 64) {
+      GMP_CUDA(cudaFuncSetAttribute(edge_feature64_tc_kernel<C, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tc64Cfg<C>::template smem<0>()));
+      GMP_CUDA(cudaFuncSetAttribute(edge_feature64_tc_kernel<C, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tc64Cfg<C>::template smem<1>()));
+      GMP_CUDA(cudaFuncSetAttribute(edge_feature64_tc_kernel<C, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tc64Cfg<C>::template smem<2>()));
+    }
     GMP_CUDA(cudaFuncSetAttribute(edge_msg_tc_kernel<E, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MsgTc<E>::kBytes));
     GMP_CUDA(cudaFuncSetAttribute(edge_msg_tc_kernel<E, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MsgTc<E>::kBytes));
     attr_done = true;
@@ -1372,6 +1448,35 @@ int run_forward(gmp_handle* h, int64_t B, const float* v, const int64_t* edge_in
       GMP_LAUNCH_CHECK();
       edge_feature_tc_kernel<C><<<std::min<int>(tile_e[B], kNumSMs), 384, TcCfg<C>::kSmemBytes, st>>>(
           W + m.w.tc_img, v, ws.csr_src, ws.csr_dst, ws.tc_unit_meta, tile_e[B], ws.tc_tables, tc_stride, use_obstacles, ws.P, ws.Q);
+      GMP_LAUNCH_CHECK();
+      tc_done = true;
+    }
+  }
+  if constexpr (E == 64) {
+    if (use_tc64 && unit_ptr[B] > 0) {
+      // tcgen05 path, embed 64: encoder -> three Block launches -> tail, the activation rows travelling through the Q buffer
+      const int64_t tc_stride = tc_off[B];
+      const int n_units = unit_ptr[B];
+      if (use_obstacles && tc_stride > 0) {
+        tc_detail::obs_table_tc64_kernel<<<dim3((unsigned)B, 3), 256, 0, st>>>(ws.tables, table_stride, ws.obs_ptr, ws.obs_tile_ptr,
+                                                                              ws.tc_tab_off, ws.tc_tables, tc_stride);
+        GMP_LAUNCH_CHECK();
+      }
+      tc_detail::unit_meta_kernel<<<(n_units + 255) / 256, 256, 0, st>>>(ws.tc_unit_ptr, (int)B, n_units, ws.edge_ptr, ws.obs_ptr,
+                                                                        ws.tc_tab_off, ws.tc_unit_meta);
+      GMP_LAUNCH_CHECK();
+      const int grid = std::min<int>(n_units, kNumSMs);
+      edge_feature64_tc_kernel<C, 0><<<grid, 384, Tc64Cfg<C>::template smem<0>(), st>>>(W + m.w.tc64_img[0], v, ws.csr_src, ws.csr_dst,
+                                                                                      ws.tc_unit_meta, n_units, nullptr, ws.Q, ws.P, ws.Q);
+      GMP_LAUNCH_CHECK();
+      for (int blk = 0; blk < (use_obstacles ? 3 : 0); ++blk) {
+        edge_feature64_tc_kernel<C, 1><<<grid, 384, Tc64Cfg<C>::template smem<1>(), st>>>(
+            W + m.w.tc64_img[1 + blk], v, ws.csr_src, ws.csr_dst, ws.tc_unit_meta, n_units, ws.tc_tables + (size_t)blk * tc_stride, ws.Q,
+            ws.P, ws.Q);
+        GMP_LAUNCH_CHECK();
+      }
+      edge_feature64_tc_kernel<C, 2><<<grid, 384, Tc64Cfg<C>::template smem<2>(), st>>>(W + m.w.tc64_img[4], v, ws.csr_src, ws.csr_dst,
+                                                                                      ws.tc_unit_meta, n_units, nullptr, ws.Q, ws.P, ws.Q);
       GMP_LAUNCH_CHECK();
       tc_done = true;
     }
@@ -1477,7 +1582,6 @@ extern "C" int gmp_explorer_set_tensor(gmp_handle* h, const char* name, const fl
 extern "C" int gmp_explorer_set_edge_feature_mode(gmp_handle* h, int mode) {
   GMP_REQUIRE(h, "null handle");
   GMP_REQUIRE(mode >= -1 && mode <= 1, "mode: -1 auto, 0 fp32 SIMT, 1 tcgen05 3xTF32");
-  GMP_REQUIRE(mode != 1 || h->ex.e == 0 || h->ex.e == 32, "the tensor-core edge-feature stage exists for embed_size 32 only");
   h->ex.edge_feature_mode = mode;
   return GMP_OK;
 }
@@ -1496,7 +1600,8 @@ extern "C" int64_t gmp_explorer_workspace_bytes(const gmp_handle* h, int64_t n_g
   // every graph may add one partially filled obstacle tile
   const int64_t obs_tiles = n_obs_total / ot + n_graphs;
   // tensor-core table rows: every sub-chunk of <= 64 obstacles is padded to a multiple of 16 rows
-  const int64_t tc_rows = h->ex.e == 32 ? n_obs_total + 16 * (n_obs_total / 48 + n_graphs) : 0;
+  // (embed 64: one chunk of <= 32 rows per graph, 4*64 floats per row -- the same bound in 4*e-float rows)
+  const int64_t tc_rows = n_obs_total + 16 * (n_obs_total / 48 + n_graphs);
   Carver cv(nullptr);
   ExWs ws;
   return carve_explorer(cv, ws, h->ex.e, n_graphs, n_nodes_total, n_edges_total, obs_tiles, tc_rows) + 256;

@@ -42,6 +42,7 @@ struct ExplorerW {
   int tc_img;                        // tensor-core image of the edge-feature stage (explorer_tc.cuh), -1 if none
   int tc_l02;                        // lin_0.2 for the tensor-core message kernel: [hi plane | lo plane | bias | pad], -1 if none
   int tc_p2;                         // policy.2 for the tensor-core policy kernel: [hi plane | lo plane | bias | policy.4 weight]
+  int tc64_img[5];                   // embed 64: phase images of explorer_tc64.cuh (encoder, Block 0..2, tail), -1 if none
 };
 
 struct ExplorerModel {

@@ -115,10 +115,11 @@ def test_errors(cuda_device):
     assert out.shape == (1, 1) and float(out.abs().sum()) == 0.0
 
 
-@pytest.mark.parametrize("tag,wfile,dims", [CASES[0], CASES[2]])
+@pytest.mark.parametrize("tag,wfile,dims", CASES)
 def test_tensor_core_edge_stage_vs_simt_and_oracle(cuda_device, tag, wfile, dims):
-    """embed 32: the tcgen05 3xTF32 edge-feature stage (default) against the fp32 SIMT stage and the oracle, on a ragged
-    batch whose obstacle counts cover 0, one partial chunk, exactly 96, two chunks (97, 130) and three chunks (200)."""
+    """The tcgen05 3xTF32 kernels (default) against the fp32 SIMT kernels and the oracle on a ragged batch.  embed 32: obstacle
+    counts cover 0, one partial chunk, exactly 96, two chunks (97, 130) and three chunks (200).  embed 64 (kuka7): the
+    phase-split stage handles up to 32 obstacles per graph (0, 1, 5, 12, 17, 31, 32 here)."""
     from oracle import explorer as o_explorer
     from oracle import knn_graph as o_knn
     sd = torch.load(os.path.join(G, "weights", wfile), map_location="cpu")
@@ -126,7 +127,8 @@ def test_tensor_core_edge_stage_vs_simt_and_oracle(cuda_device, tag, wfile, dims
     c, s = dims[1], dims[3]
     rng = np.random.default_rng(7)
     graphs = []
-    for n, k, o in [(300, 12, 96), (40, 5, 0), (513, 9, 97), (129, 20, 5), (260, 8, 130), (64, 6, 200), (700, 10, 57)]:
+    obs_counts = [96, 0, 97, 5, 130, 200, 57] if dims[2] == 32 else [32, 0, 17, 5, 1, 31, 12]
+    for (n, k), o in zip([(300, 12), (40, 5), (513, 9), (129, 20), (260, 8), (64, 6), (700, 10)], obs_counts):
         v = rng.uniform(-1, 1, (n, c)).astype(np.float32)
         ei = o_knn.knn_graph_edges(v, n, k)
         obs = rng.uniform(-0.5, 0.5, (o, s)).astype(np.float32)

@@ -564,9 +564,10 @@ def main():
                    "kernel it replaces peaked at 148 SM x 128 FMA x %.0f MHz = %.1f TFLOP/s"
                    % (peak_tf / 6.0, ef_tflops / (peak_tf / 6.0), sm_mhz, fp32_peak_tf))
     else:
-        ef_kernel = "edge_feature_kernel<%d,%d>" % (c, wl["e"])
-        ef_note = ("fp32 FMA kernel (1e-4 logit tolerance rules out 1-pass TF32/BF16; the tcgen05 3xTF32 stage exists for e = 32); vs "
-                   "fp32 SIMT peak 148 SM x 128 FMA x %.0f MHz = %.1f TFLOP/s the fraction is %.3f" % (sm_mhz, fp32_peak_tf, ef_tflops / fp32_peak_tf))
+        # embed 64: the phase-split tcgen05 stage (encoder, Block x3, tail = 5 launches; graphs here have <= 32 obstacles)
+        ef_kernel = "edge_feature64_tc_kernel<%d,phase 0|1|1|1|2>" % c
+        ef_note = ("five launches of the phase-split tcgen05 3xTF32 stage, timed together (ms_per_launch = the whole stage); against "
+                   "the 3xTF32 ceiling (bf16 peak / 6 = %.0f TFLOP/s) the fraction is %.3f" % (peak_tf / 6.0, ef_tflops / (peak_tf / 6.0)))
     line = {
         "metric": "explorer_graphs_per_sec", "value": graphs_per_s, "unit": "graphs/s", "n_gpus": world, "steps": K,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -591,9 +592,9 @@ def main():
         "e2e": {"value": B * world / (ms_e2e / 1000.0), "unit": "graphs/s", "h2d_bytes_per_step": io["h2d"], "d2h_bytes_per_step": io["d2h"],
                 "ms_per_step": ms_e2e, "api": "gnn_motion_planning_b200.batch.HotPath.submit/wait (double-buffered; read-back of "
                                               "step k overlaps the kernels of step k+1)"},
-        "gpu_launches": K * (5 + 3 + 1 + 1 + 1 + (3 if wl["e"] == 32 else 1) + 6 + 5 + 1 + 1 + 1),
+        "gpu_launches": K * (5 + 3 + 1 + 1 + 1 + (3 if wl["e"] == 32 else 7) + 6 + 5 + 1 + 1 + 1),
         "gpu_launches_note": "per step: knn 5 (select,row_count,row_scan,graph_scan,emit) + csr 3 + goal_index + obstacle + node_pre + "
-                             "edge_feature (e=32: obs_table_tc + unit_meta + edge_feature_tc) + node_loop x6 + edge_msg x5 + policy + "
+                             "edge_feature (e=32: obs_table_tc + unit_meta + edge_feature_tc; e=64: obs_table_tc64 + unit_meta + 5 phases) + node_loop x6 + edge_msg x5 + policy + "
                              "{maze,arm}_edge_graph + result_rows; memsets/copies not counted",
         "clocks": clocks,
     }

@@ -211,6 +211,13 @@ __global__ void __launch_bounds__(384, 1) edge_feature64_tc_kernel(
     auto prefetch_unit = [&](int u) {
       if (u < n_units) {
         meta_nx = __ldg(unit_meta + u);
+        if (PHASE != 0) {
+          // the next unit's activation row comes from HBM (written by the previous launch): pull it into L2 now
+          const int sl = min(meta_nx.x + tile * 128 + row, meta_nx.y - 1);
+          const float* nx = xio + (size_t)sl * E;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + 32));
+        }
         if (PHASE != 1) {
           const int sl = meta_nx.x + tile * 128 + row;
           const bool ok = sl < meta_nx.y;

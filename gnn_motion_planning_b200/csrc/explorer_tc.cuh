@@ -636,9 +636,12 @@ __global__ void __launch_bounds__(384, 1) edge_feature_tc_kernel(
 // result comes back with tcgen05.ld.  Tiles are 128 rows (one MMA); each CTA owns 128 TMEM columns, four CTAs per SM.
 template <int E_>
 struct MsgTc {
-  static constexpr int E = E_, R = 128, RP = R + 1;
+  static constexpr int E = E_, R = 128, XP = E + 4;   // XP: row pitch of the hidden / message tile (floats)
   static constexpr int kPS = R * E;              // staged P tile (row-major)
-  static constexpr int kX = E * RP;              // hidden / message tile, feature-major
+  // hidden / message tile, ROW-major with a 4-float pad: the 8-lanes-per-row gather stores float4s, the thread-per-row
+  // readers load float4s (a quarter warp = 8 rows, 16 B each, 144 B apart: all 32 banks), the (feature, row group) scan reads
+  // 32 consecutive floats -- every access conflict-free, a quarter of the LSU instructions of a feature-major tile
+  static constexpr int kX = R * XP;
   static constexpr int kW = 2 * E * E + 2 * E;   // lin_0[2] / policy[2]: hi plane | lo plane | bias | (policy[4] weight)
   static constexpr size_t kNeed = (size_t)(kPS + kX + kW) * sizeof(float) + 2 * R * sizeof(int);
   // tensor memory: XH | XL | D = 3E columns, allocated as a power of two; kCtas CTAs per SM share the 512 columns.  The
@@ -666,7 +669,7 @@ __global__ void __launch_bounds__(128, MsgTc<E_>::kCtas) edge_msg_tc_kernel(cons
                                                              const float* __restrict__ A, const float* __restrict__ B,
                                                              const float* __restrict__ P, float* __restrict__ AGG, PolicyOut po) {
   using M = MsgTc<E_>;
-  constexpr int E = M::E, R = M::R, RP = M::RP;
+  constexpr int E = M::E, R = M::R, XP = M::XP;
   constexpr int LPR = E / 4, RPP = 128 / LPR;
   extern __shared__ __align__(128) float smem_msg[];
   float* PS = smem_msg;                       // first: 128 B aligned for the bulk copy
@@ -734,11 +737,12 @@ __global__ void __launch_bounds__(128, MsgTc<E_>::kCtas) edge_msg_tc_kernel(cons
         const int r = base + rsub + u * RPP;
         const float4 p = *reinterpret_cast<const float4*>(PS + r * E + 4 * q);
         const bool ok = sv[u] >= 0;
-        float* x = X + (4 * q) * RP + r;
-        x[0] = ok ? fmaxf(av[u].x + bv[u].x + p.x, 0.0f) : 0.0f;
-        x[RP] = ok ? fmaxf(av[u].y + bv[u].y + p.y, 0.0f) : 0.0f;
-        x[2 * RP] = ok ? fmaxf(av[u].z + bv[u].z + p.z, 0.0f) : 0.0f;
-        x[3 * RP] = ok ? fmaxf(av[u].w + bv[u].w + p.w, 0.0f) : 0.0f;
+        float4 hv;
+        hv.x = ok ? fmaxf(av[u].x + bv[u].x + p.x, 0.0f) : 0.0f;
+        hv.y = ok ? fmaxf(av[u].y + bv[u].y + p.y, 0.0f) : 0.0f;
+        hv.z = ok ? fmaxf(av[u].z + bv[u].z + p.z, 0.0f) : 0.0f;
+        hv.w = ok ? fmaxf(av[u].w + bv[u].w + p.w, 0.0f) : 0.0f;
+        *reinterpret_cast<float4*>(X + r * XP + 4 * q) = hv;
       }
     }
     __syncthreads();           // X complete; staging buffer consumed
@@ -751,7 +755,10 @@ __global__ void __launch_bounds__(128, MsgTc<E_>::kCtas) edge_msg_tc_kernel(cons
       // this thread's hidden row -> TF32 hi / lo planes in TMEM (the A operand)
       float h[E];
 #pragma unroll
-      for (int k = 0; k < E; ++k) h[k] = X[k * RP + threadIdx.x];
+      for (int k = 0; k < E; k += 4) {
+        const float4 t4 = *reinterpret_cast<const float4*>(X + threadIdx.x * XP + k);
+        h[k] = t4.x; h[k + 1] = t4.y; h[k + 2] = t4.z; h[k + 3] = t4.w;
+      }
       umma::st_split<E>(trow + M::cXH, trow + M::cXL, h);
       umma::wait_st();
     }
@@ -801,7 +808,9 @@ __global__ void __launch_bounds__(128, MsgTc<E_>::kCtas) edge_msg_tc_kernel(cons
       tc_detail::ld_cols<E>(trow + M::cD, mrow);
       umma::wait_ld();
 #pragma unroll
-      for (int n = 0; n < E; ++n) X[n * RP + threadIdx.x] = mrow[n] + bias[n];
+      for (int n = 0; n < E; n += 4)
+        *reinterpret_cast<float4*>(X + threadIdx.x * XP + n) =
+            make_float4(mrow[n] + bias[n], mrow[n + 1] + bias[n + 1], mrow[n + 2] + bias[n + 2], mrow[n + 3] + bias[n + 3]);
     }
     umma::fence_before_sync();
     __syncthreads();
@@ -820,7 +829,7 @@ __global__ void __launch_bounds__(128, MsgTc<E_>::kCtas) edge_msg_tc_kernel(cons
         cur = d;
         run = -INFINITY;
       }
-      run = fmaxf(run, X[n * RP + r0 + i]);
+      run = fmaxf(run, X[(r0 + i) * XP + n]);
     }
     if (cur >= 0) atomic_max_f32(AGG + (size_t)cur * E + n, run);
     // (the loop-top barrier protects IDX / X; tensor memory is rewritten only after the next tile's barriers)

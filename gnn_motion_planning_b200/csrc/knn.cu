@@ -122,8 +122,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) knn_select_kernel(
 // Register-strip variant for graphs with at most 32*NPL nodes (the BASELINE sizes: 1000 -> NPL 32, 2000 -> NPL 64):
 // each lane keeps the bit patterns of its NPL candidate distances in registers, so the 31 bisection passes are pure
 // ALU work (no shared-memory re-reads -- the strip version is bound by the single LSU port).  Same selection rule.
+// Register budget: the strip (NPL registers) plus a few temporaries.  Left to itself ptxas unrolls the 31 bisection passes and
+// takes 223 registers (one 8-warp CTA per SM, issue slots 47 % busy -- ncu, profiles/r1_knn_select_ncu.txt); capping the
+// registers and keeping the bit loop rolled gives 3-5 CTAs per SM.
 template <int NPL>
-__global__ void __launch_bounds__(kWarpsPerCta * 32) knn_select_reg_kernel(
+__global__ void __launch_bounds__(kWarpsPerCta * 32, NPL <= 16 ? 5 : (NPL <= 32 ? 3 : 2)) knn_select_reg_kernel(
     const float* __restrict__ v, int c, const int32_t* __restrict__ node_ptr, const int32_t* __restrict__ n_free,
     const int32_t* __restrict__ k1s, const int64_t* __restrict__ bm_ptr, int n_graphs, int n_rows_total,
     uint32_t* __restrict__ bitmap) {
@@ -164,12 +167,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) knn_select_reg_kernel(
     int n_less = cnt;
     if (k < cnt) {
       T = 0;
+#pragma unroll 1
       for (int bit = 30; bit >= 0; --bit) {
         const uint32_t cand = T | (1u << bit);
-        int cl = 0;
+        int c0 = 0, c1 = 0, c2 = 0, c3 = 0;   // four independent count chains
 #pragma unroll
-        for (int t = 0; t < NPL; ++t) cl += (d[t] < cand) ? 1 : 0;
-        cl = __reduce_add_sync(0xffffffffu, cl);
+        for (int t = 0; t < NPL; t += 4) {
+          c0 += (d[t] < cand) ? 1 : 0; c1 += (d[t + 1] < cand) ? 1 : 0; c2 += (d[t + 2] < cand) ? 1 : 0; c3 += (d[t + 3] < cand) ? 1 : 0;
+        }
+        const int cl = __reduce_add_sync(0xffffffffu, (c0 + c1) + (c2 + c3));
         if (cl < k) T = cand;
       }
       int cl = 0;

@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) knn_select_kernel(
 // takes 223 registers (one 8-warp CTA per SM, issue slots 47 % busy -- ncu, profiles/r1_knn_select_ncu.txt); capping the
 // registers and keeping the bit loop rolled gives 3-5 CTAs per SM.
 template <int NPL>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, NPL <= 16 ? 5 : (NPL <= 32 ? 3 : 2)) knn_select_reg_kernel(
+__global__ void __launch_bounds__(kWarpsPerCta * 32, NPL <= 16 ? 5 : (NPL <= 32 ? 4 : 2)) knn_select_reg_kernel(
     const float* __restrict__ v, int c, const int32_t* __restrict__ node_ptr, const int32_t* __restrict__ n_free,
     const int32_t* __restrict__ k1s, const int64_t* __restrict__ bm_ptr, int n_graphs, int n_rows_total,
     uint32_t* __restrict__ bitmap) {

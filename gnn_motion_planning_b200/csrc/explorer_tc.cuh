@@ -313,6 +313,7 @@ __global__ void __launch_bounds__(384, 1) edge_feature_tc_kernel(
           if (sc == 0) {
             GMP_TC_STAGE(2, {
               umma::gemm3_fixed<64, E, 64>(tc + Cf::cA1, xh, xl, gv_h, gv_l, false);
+              umma::commit(&bar_done[t]);   // Gx | Vx can be read (self score) while the scores are still being computed
               umma::gemm3_n<E>(tc + Cf::cSC, xh, xl, mt_h0, mt_l0, per);
               if (ns == 2) umma::gemm3_n<E>(tc + Cf::cSC1, xh, xl, mt_h1, mt_l1, per);
             });
@@ -539,6 +540,7 @@ __global__ void __launch_bounds__(384, 1) edge_feature_tc_kernel(
           m = mnew;
           return corr;
         };
+        if (nch > 0) await(0);   // scores of the first one or two sub-chunks (committed separately from Gx | Vx)
         for (int s2 = 0; 2 * s2 < nch; ++s2) {
           const int ns = min(2, nch - 2 * s2);
           if (s2 > 0) {

@@ -816,22 +816,31 @@ __global__ void __launch_bounds__(128, MsgTc<E_>::kCtas) edge_msg_tc_kernel(cons
     }
     umma::fence_before_sync();
     __syncthreads();
-    // segmented max: thread = (feature n, row group); rows of a group are walked in CSR order, so a
-    // target's rows are consecutive; one RED per (segment, feature), 128 B coalesced across the warp.
+    // segmented max: thread = (feature n, row group); rows of a group are walked in CSR order, so a target's rows are
+    // consecutive; one RED per (segment, feature), 128 B coalesced across the warp.  Every lane of a warp walks the same
+    // rows: the segment heads are found once per 32 rows (one target id per lane, shuffle + ballot) instead of re-reading
+    // the id of every row -- the scan is then one shared-memory load per row.
     constexpr int GROUPS = 128 / E;
     constexpr int ROWS = R / GROUPS;
     const int n = threadIdx.x % E;
     const int r0 = (threadIdx.x / E) * ROWS;
-    int cur = IDX[r0];
+    const int lane = threadIdx.x & 31;
+    int cur = -1;
     float run = -INFINITY;
-    for (int i = 0; i < ROWS; ++i) {
-      const int d = IDX[r0 + i];
-      if (d != cur) {
-        if (cur >= 0) atomic_max_f32(AGG + (size_t)cur * E + n, run);
-        cur = d;
-        run = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < ROWS / 32; ++c) {
+      const int dl = IDX[r0 + 32 * c + lane];
+      int prev = __shfl_up_sync(0xffffffffu, dl, 1);
+      if (lane == 0) prev = cur;   // (cur is warp-uniform: the target of the previous chunk's last row, -1 at the start)
+      const uint32_t heads = __ballot_sync(0xffffffffu, dl != prev);
+      for (int i = 0; i < 32; ++i) {
+        if ((heads >> i) & 1u) {
+          if (cur >= 0) atomic_max_f32(AGG + (size_t)cur * E + n, run);
+          cur = __shfl_sync(0xffffffffu, dl, i);
+          run = -INFINITY;
+        }
+        run = fmaxf(run, X[(r0 + 32 * c + i) * XP + n]);
       }
-      run = fmaxf(run, X[(r0 + i) * XP + n]);
     }
     if (cur >= 0) atomic_max_f32(AGG + (size_t)cur * E + n, run);
     // (the loop-top barrier protects IDX / X; tensor memory is rewritten only after the next tile's barriers)

@@ -248,7 +248,9 @@ __global__ void __launch_bounds__(384, 1) edge_feature_tc_kernel(
       }
       const int O = meta_cur.z;
       const int nch = n_blocks ? tc_nchunks(O) : 0, per = tc_per(O, nch);
-      // one stage for both tiles: wait for the tile's operands, issue, commit
+      // one stage for both tiles: wait for the tile's operands, issue, commit.  Exactly ONE commit per `ready` phase: a
+      // `done` phase must be observed by all 128 waiters before the next one can complete (mbarrier waits are by parity; a
+      // second commit without a publish in between could complete two phases behind a slow warp's back and hang it)
 #ifdef GMP_TC_PROFILE
 #define GMP_TC_T0 const long long w0 = clock64();
 #define GMP_TC_T1 prof_ready[t] += clock64() - w0;
@@ -313,7 +315,6 @@ __global__ void __launch_bounds__(384, 1) edge_feature_tc_kernel(
           if (sc == 0) {
             GMP_TC_STAGE(2, {
               umma::gemm3_fixed<64, E, 64>(tc + Cf::cA1, xh, xl, gv_h, gv_l, false);
-              umma::commit(&bar_done[t]);   // Gx | Vx can be read (self score) while the scores are still being computed
               umma::gemm3_n<E>(tc + Cf::cSC, xh, xl, mt_h0, mt_l0, per);
               if (ns == 2) umma::gemm3_n<E>(tc + Cf::cSC1, xh, xl, mt_h1, mt_l1, per);
             });
@@ -540,7 +541,6 @@ __global__ void __launch_bounds__(384, 1) edge_feature_tc_kernel(
           m = mnew;
           return corr;
         };
-        if (nch > 0) await(0);   // scores of the first one or two sub-chunks (committed separately from Gx | Vx)
         for (int s2 = 0; 2 * s2 < nch; ++s2) {
           const int ns = min(2, nch - 2 * s2);
           if (s2 > 0) {

@@ -160,3 +160,38 @@ def test_tensor_core_edge_stage_vs_simt_and_oracle(cuda_device, tag, wfile, dims
             assert err < TOL, (tag, g, mode, err)
     print("tc vs simt max |diff| %.3g; worst |err| vs fp64 oracle %.3g" % (np.abs(out["tc"] - out["simt"]).max(), worst))
     assert np.abs(out["tc"] - out["simt"]).max() < TOL
+
+
+def test_forward_is_stable_under_concurrent_streams(cuda_device):
+    """The tensor-core kernels synchronise through mbarrier phases; a protocol slip shows up as a hang (trap) or a wrong
+    result only when warps are delayed.  Run the forward repeatedly while a second stream keeps the SMs busy with k-NN
+    graph builds: every repetition must reproduce the first result bit for bit."""
+    from gnn_motion_planning_b200 import graph
+    from oracle import knn_graph as o_knn
+    m = make_model("weights_maze.pt", (2, 2, 32, 2), cuda_device)
+    rng = np.random.default_rng(3)
+    B, n, k = 12, 700, 20
+    vs, eis, obs = [], [], []
+    for g in range(B):
+        v = rng.uniform(-1, 1, (n, 2)).astype(np.float32)
+        vs.append(v)
+        eis.append(o_knn.knn_graph_edges(v, n, k))
+        obs.append(rng.uniform(-0.5, 0.5, (60 + 7 * g, 2)).astype(np.float32))     # 60 .. 137 obstacles: lone chunks and pairs
+    node_ptr = np.arange(B + 1) * n
+    edge_ptr = np.cumsum([0] + [e.shape[1] for e in eis])
+    obs_ptr = np.cumsum([0] + [len(o) for o in obs])
+    V = torch.from_numpy(np.concatenate(vs)).to(cuda_device)
+    EI = torch.from_numpy(np.concatenate(eis, 1)).to(cuda_device)
+    GOAL = torch.from_numpy(np.stack([v[1] for v in vs])).to(cuda_device)
+    OBS = torch.from_numpy(np.concatenate(obs)).to(cuda_device)
+    first = m.forward_batch(V, EI, GOAL, OBS, node_ptr, edge_ptr, obs_ptr, loop=5).clone()
+    side = torch.cuda.Stream(device=cuda_device)
+    npt = np.arange(B + 1, dtype=np.int32) * n
+    side.wait_stream(torch.cuda.current_stream(cuda_device))
+    for rep in range(12):
+        out = m.forward_batch(V, EI, GOAL, OBS, node_ptr, edge_ptr, obs_ptr, loop=5)     # asynchronous on the current stream
+        with torch.cuda.stream(side):                                                   # ... while the side stream builds graphs
+            for _ in range(3):
+                graph.knn_graph_batch(V, npt, np.full(B, n, np.int32), np.full(B, k, np.int32))
+        assert torch.equal(out, first), rep
+    torch.cuda.synchronize()

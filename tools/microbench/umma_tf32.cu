@@ -1,7 +1,11 @@
 // Microbenchmark / bring-up test of the tcgen05 primitives in csrc/umma.cuh (B200 only):
-//   1. D = A.B^T with A in shared memory (SS) and in TMEM (TS), 1xTF32 and 3xTF32, error against fp64;
+//   1. MMA issue patterns: n back-to-back tcgen05.mma (M = 128, K = 8) from one or two issuing warps, operands in uniform
+//      registers (warp-uniform branch + elect.sync): 128*N/256 cycles per MMA.  (Issued from a divergent branch with
+//      per-thread values ptxas emits an ELECT / R2UR waterfall per MMA: ~62 cycles each regardless of N.)
+//   2. D = A.B^T with A in shared memory (SS) and in TMEM (TS), 1xTF32 and 3xTF32, error against fp64;
 //      tells whether operand conversion truncates and how close 3xTF32 gets to fp32;
-//   2. cycle counts: MMA group issue -> commit latency, tcgen05.ld / tcgen05.st throughput with 4 and 8 warps.
+//   3. cycle counts: MMA group issue -> commit latency, tcgen05.ld / tcgen05.st throughput with 4 and 8 warps.
+// Results of the run this library was designed around: profiles/r1_umma_tf32_microbench.log.
 // Build + run on the GPU box:
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I gnn_motion_planning_b200/csrc \
 //        -o tools/microbench/umma_tf32 tools/microbench/umma_tf32.cu && tools/microbench/umma_tf32

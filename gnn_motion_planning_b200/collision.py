@@ -174,8 +174,10 @@ def arm_edge_fp_graph(model, v, edge_index, node_ptr_d, edge_ptr_d, boxes, box_p
     checks = checks_out
     if want_checks and checks is None:
         checks = torch.empty(n_edges_total, dtype=torch.int32, device=v.device)
-    _lib.check(lib.gmp_arm_edge_fp_graph(int(model), _lib.ptr(v), _lib.ptr(edge_index), edge_index.stride(0), _lib.ptr(node_ptr_d),
-                                         _lib.ptr(edge_ptr_d), _lib.ptr(problem_of_graph), B, n_edges_total, _lib.ptr(boxes),
-                                         _lib.ptr(box_ptr), float(rrt_eps), _lib.ptr(free), _lib.ptr(checks),
-                                         _lib.stream_ptr(v.device)))
+    # endpoint states are checked once per node (cached form): same booleans and counts, ~3 of (2 + K) evaluations per edge fewer
+    flags = torch.empty(max(v.shape[0], 1), dtype=torch.uint8, device=v.device)
+    _lib.check(lib.gmp_arm_edge_fp_graph_cached(int(model), _lib.ptr(v), v.shape[0], _lib.ptr(edge_index), edge_index.stride(0),
+                                                _lib.ptr(node_ptr_d), _lib.ptr(edge_ptr_d), _lib.ptr(problem_of_graph), B, n_edges_total,
+                                                _lib.ptr(boxes), _lib.ptr(box_ptr), float(rrt_eps), _lib.ptr(flags), _lib.ptr(free),
+                                                _lib.ptr(checks), _lib.stream_ptr(v.device)))
     return (free, checks) if want_checks else free

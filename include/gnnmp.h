@@ -161,6 +161,14 @@ int gmp_arm_edge_fp_graph(int model, const float* v, const int64_t* edge_index, 
                           const int32_t* node_ptr, const int32_t* edge_ptr, const int32_t* problem_of_graph,
                           int64_t n_graphs, int64_t n_edges_total, const double* boxes, const int32_t* box_ptr,
                           double rrt_eps, uint8_t* free_out, int32_t* n_checks_out, void* stream);
+/* The same result (booleans and check counts, bit for bit) with the endpoint checks evaluated once per NODE instead of once per
+ * incident edge: every edge check starts with both endpoint states and repeats the start state at k = 0 (kuka_env.py:394-409),
+ * and in a k-NN graph each node is an endpoint of ~2k edges.  node_flags_ws: n_nodes_total bytes of device scratch. */
+int gmp_arm_edge_fp_graph_cached(int model, const float* v, int64_t n_nodes_total, const int64_t* edge_index,
+                                 int64_t edge_row_stride, const int32_t* node_ptr, const int32_t* edge_ptr,
+                                 const int32_t* problem_of_graph, int64_t n_graphs, int64_t n_edges_total, const double* boxes,
+                                 const int32_t* box_ptr, double rrt_eps, uint8_t* node_flags_ws, uint8_t* free_out,
+                                 int32_t* n_checks_out, void* stream);
 
 /* ---- smoother: ModelSmoother (model_smoother.py:46-142) --------------------------------------- */
 int gmp_smoother_init(gmp_handle* h, int config_size /*c*/, int embed_size /*128*/);

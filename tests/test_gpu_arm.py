@@ -56,6 +56,7 @@ def test_edge_graph_matches_explicit(cuda_device, probs):
     rng = np.random.default_rng(5)
     B, n = 4, 150
     v = rng.uniform(lo, hi, (B * n, 7)).astype(np.float32)
+    v[[5, 170, 171, 449]] *= 3.0          # a few nodes outside the joint limits (the graph form caches per-node validity / freeness)
     es = [rng.integers(0, n, (2, 500 + 7 * g)) for g in range(B)]
     edge_ptr = np.cumsum([0] + [e.shape[1] for e in es]).astype(np.int32)
     node_ptr = (np.arange(B + 1) * n).astype(np.int32)

@@ -350,7 +350,9 @@ def run_reference(args, wl, rank, world):
 def workload_config(args, wl, world):
     return {"workload": "%s: %s, batch=%d problems/GPU, %d-node k=%d RGG, loop=5, shipped %s" % (
         args.workload, wl["env"], wl["batch"], wl["n"], wl["k"], wl["weights"]),
-        "step": "knn_graph + explorer_forward + edge collision check of all edges", "global_batch": wl["batch"] * world,
+        "step": "knn_graph + explorer_forward + edge collision check of all edges" + (
+            " + smoother forward x5 on a 24-waypoint path per problem" if wl["env"] == "kuka7" and wl["n"] >= 1000 else ""),
+        "global_batch": wl["batch"] * world,
         "parallelism": "dp%d (independent problems sharded, all-gather of result rows only)" % world,
         "l2": "per-step working set (~3.8 GB of edge features) >> 126 MB L2; no explicit flush needed"}
 
@@ -447,14 +449,46 @@ def main():
     phase_ms = {}
     state = {}
 
+    # ---- smoother forward (model_smoother.py:104-142), as model_smooth drives it: 5 x loop=1 on a path (smoother.py:233-246).
+    # Synthetic path per problem: init (node 0), nodes 2..P-1, goal (node 1); samples = the problem's first 500 nodes as free and
+    # the next 500 as collided (smoother.py:57-58 truncation); chain both ways + self loops (smoother.py:238-241).
+    sm = None
+    smooth_w = {"kuka7": ("smooth_7d_attv3.pt", 3)}.get(wl["env"])   # BASELINE configs[2] names the smoother; configs[1] is explorer only
+    if smooth_w and N >= 1000:
+        from gnn_motion_planning_b200.model_smoother import ModelSmoother
+        sm = ModelSmoother(workspace_size=3, config_size=c, obs_size=6, embed_size=128).to(dev)   # (both sizes unused by the live forward)
+        sm.load_state_dict(torch.load(os.path.join(G, "weights", smooth_w[0]), map_location="cpu"))
+        sm.eval()
+        P = 24
+        idx = torch.tensor([0] + list(range(2, P)) + [1], device=dev)
+        sm_path0 = v_d.view(B, N, c)[:, idx, :].reshape(B * P, c).contiguous()
+        sm_samples = v_d.view(B, N, c)[:, :1000, :].reshape(B * 1000, c).contiguous()
+        a_ = np.arange(P - 1)
+        ei1 = np.concatenate([np.stack([a_, a_ + 1]), np.stack([a_ + 1, a_]), np.stack([np.arange(P), np.arange(P)])], 1)
+        sm_ei = torch.from_numpy(np.tile(ei1, (1, B)).astype(np.int64)).to(dev)
+        sm_args = (np.arange(B + 1) * P, np.arange(B + 1) * 1000, np.full(B, 500), np.arange(B + 1) * ei1.shape[1])
+
+    def run_smoother():
+        p_ = sm_path0
+        for _ in range(5):
+            p_ = sm.forward_batch(p_, sm_samples, sm_ei, sm_args[0], sm_args[1], sm_args[2], sm_args[3], loop=1)
+        return p_
+
     def step(timed=False):
         evs = [ev() for _ in range(4)]
         bufs = hp.compute(v_d, goal_d, obs_d, obs_ptr, prob_d, events=evs)
         if world > 1:   # the only collective: per-problem result rows
             dist.all_gather_into_tensor(gather_buf.view(world * B, 4), bufs["rows"])
         state.update(et=bufs["et"], edge_ptr=bufs["edge_ptr"], rows=bufs["rows"], checks=bufs["checks"])
+        if sm is not None:
+            se = (ev(), ev())
+            se[0].record()
+            state["smooth_path"] = run_smoother()
+            se[1].record()
         if timed:
             torch.cuda.current_stream().synchronize()
+            if sm is not None:
+                phase_ms["smoother_forward_x5"] = phase_ms.get("smoother_forward_x5", 0.0) + se[0].elapsed_time(se[1])
             for k_, v_ in model.last_timings().items():
                 phase_ms[k_] = phase_ms.get(k_, 0.0) + v_
             phase_ms["knn_graph"] = phase_ms.get("knn_graph", 0.0) + evs[0].elapsed_time(evs[1])
@@ -499,6 +533,8 @@ def main():
 
     def e2e_step():
         t = hp.submit(v_h, goal_h, obs_h, obs_ptr, prob_h, maps_h=maps_h if is_maze else None)
+        if sm is not None:
+            state["smooth_path"] = run_smoother()
         if world > 1:
             dist.all_gather_into_tensor(gather_buf.view(world * B, 4), t["rows"])
         pending.append(t)
@@ -592,10 +628,10 @@ def main():
         "e2e": {"value": B * world / (ms_e2e / 1000.0), "unit": "graphs/s", "h2d_bytes_per_step": io["h2d"], "d2h_bytes_per_step": io["d2h"],
                 "ms_per_step": ms_e2e, "api": "gnn_motion_planning_b200.batch.HotPath.submit/wait (double-buffered; read-back of "
                                               "step k overlaps the kernels of step k+1)"},
-        "gpu_launches": K * (5 + 3 + 1 + 1 + 1 + (3 if wl["e"] == 32 else 7) + 6 + 5 + 1 + 1 + 1),
+        "gpu_launches": K * (5 + 3 + 1 + 1 + 1 + (3 if wl["e"] == 32 else 7) + 6 + 5 + 1 + 1 + 1 + (20 if sm is not None else 0)),
         "gpu_launches_note": "per step: knn 5 (select,row_count,row_scan,graph_scan,emit) + csr 3 + goal_index + obstacle + node_pre + "
                              "edge_feature (e=32: obs_table_tc + unit_meta + edge_feature_tc; e=64: obs_table_tc64 + unit_meta + 5 phases) + node_loop x6 + edge_msg x5 + policy + "
-                             "{maze,arm}_edge_graph + result_rows; memsets/copies not counted",
+                             "{maze,arm}_edge_graph (arms: node_flags + edge_graph_cached) + result_rows + smoother 5 x (graph,node,msg,path); memsets/copies not counted",
         "clocks": clocks,
     }
     if world == 1 and not args.no_cpu_baseline:

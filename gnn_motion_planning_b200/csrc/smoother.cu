@@ -176,9 +176,11 @@ __global__ void __launch_bounds__(kRtThreads) smoother_node_kernel(SmootherW w, 
   float in[1][C + 3];
 #pragma unroll
   for (int k = 0; k < C + 3; ++k) in[0][k] = 0.0f;
+  bool is_path = false;
   if (valid) {
     const int g = find_segment(nd_ptr, n_graphs, row);
     const int local = row - nd_ptr[g];
+    is_path = local < path_len[g];
 #pragma unroll
     for (int k = 0; k < C; ++k) in[0][k] = nodes[(size_t)row * C + k];
     const int kind = local < path_len[g] ? 0 : (local < path_len[g] + free_len[g] ? 1 : 2);   // model_smoother.py:130-133
@@ -204,6 +206,9 @@ __global__ void __launch_bounds__(kRtThreads) smoother_node_kernel(SmootherW w, 
   acc_zero(acc);
   gemm_smem<kE, kE, 1, RP>(acc, xcol, sm.WB);
   if (valid) acc_store_global<1, kE>(acc, 0, A + (size_t)row * kE);
+  // B = (W3-W1) x + b is read for message TARGETS only, and only path nodes are targets (model_smoother.py:125-126: the k-NN
+  // edges run sample -> path): tiles without a path row (7 of 8 at 1000 samples per problem) skip the product
+  if (!__syncthreads_or(is_path ? 1 : 0)) return;
   stage_load(sm.WB, W + w.l0_B, kE * kE + kE);
   acc_zero(acc);
   gemm_smem<kE, kE, 1, RP>(acc, xcol, sm.WB);

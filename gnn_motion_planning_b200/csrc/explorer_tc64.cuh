@@ -271,18 +271,15 @@ __global__ void __launch_bounds__(384, 1) edge_feature64_tc_kernel(
         const float* bv = img + Cf::p1VEC;
         const int per = tc_per(O, O > 0);
         float acc[E];
+        float x[E];   // the Block's input row: A operand, self score, residual
         float m, l = 1.0f;
-        {
-          float x[E];
-          load_row(xrow, x);
-          umma::st_split<E>(xh, xl, x);
-        }
+        load_row(xrow, x);
+        umma::st_split<E>(xh, xl, x);
         publish();
         await();   // Gx | Vx
         {
-          float u[E], x[E];
+          float u[E];
           tc_detail::ld_cols<E>(a1, u);
-          load_row(xrow, x);
           umma::wait_ld();
           float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
@@ -328,8 +325,6 @@ __global__ void __launch_bounds__(384, 1) edge_feature64_tc_kernel(
           for (int n = 0; n < E; ++n) acc[n] = fmaf(acc[n], corr, pv[n]);
         }
         {
-          float x[E];
-          load_row(xrow, x);
           const float inv = 1.0f / l;
 #pragma unroll
           for (int n = 0; n < E; ++n) acc[n] = fmaf(acc[n], inv, x[n]);

@@ -394,19 +394,18 @@ __global__ void __launch_bounds__(384, 1) edge_feature_tc_kernel(
       prof_kind = kind;
 #endif
     };
-    // this unit's metadata and edge endpoints are fetched one unit ahead (their latency hides behind the previous unit)
-    int4 meta_nx = make_int4(0, 0, 0, 0);
+    // two units of metadata and one unit of endpoints are kept in flight, so that no load of the chain
+    // meta -> CSR endpoints -> node coordinates ever waits on the one before it
+    auto load_meta = [&](int u) { return u < n_units ? __ldg(unit_meta + u) : make_int4(0, 0, 0, 0); };
+    int4 meta_nx = load_meta(blockIdx.x), meta_nx2 = load_meta(blockIdx.x + gridDim.x);
     int s_nx = 0, d_nx = 0;
-    auto prefetch_unit = [&](int u) {
-      if (u < n_units) {
-        meta_nx = __ldg(unit_meta + u);
-        const int sl = meta_nx.x + tile * 128 + row;
-        const bool ok = sl < meta_nx.y;
-        s_nx = ok ? __ldg(csr_src + sl) : 0;
-        d_nx = ok ? __ldg(csr_dst + sl) : 0;
-      }
+    auto load_endpoints = [&](const int4 mm) {
+      const int sl = mm.x + tile * 128 + row;
+      const bool ok = sl < mm.y;
+      s_nx = ok ? __ldg(csr_src + sl) : 0;
+      d_nx = ok ? __ldg(csr_dst + sl) : 0;
     };
-    prefetch_unit(blockIdx.x);
+    load_endpoints(meta_nx);
     for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
       const int4 meta = meta_nx;
       const int slot = meta.x + tile * 128 + row;
@@ -414,7 +413,9 @@ __global__ void __launch_bounds__(384, 1) edge_feature_tc_kernel(
       const int O = meta.z;
       const int nch = n_blocks ? tc_nchunks(O) : 0, per = tc_per(O, nch);
       const int s_node = s_nx, d_node = d_nx;
-      prefetch_unit(unit + gridDim.x);
+      meta_nx = meta_nx2;                                  // next unit: its metadata arrived a unit ago ...
+      load_endpoints(meta_nx);                             // ... so its endpoints can be requested right away
+      meta_nx2 = load_meta(unit + 2 * gridDim.x);
       auto gather = [&](float* in) {   // cat(v[src], v[dst]), zero padded to K0
 #pragma unroll
         for (int k = 0; k < K0; ++k) in[k] = 0.f;

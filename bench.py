@@ -621,9 +621,9 @@ def main():
                      "peak_source": peak_src,
                      "ms_per_launch": ef_ms, "algorithmic_gflop_per_launch": ef_flops / 1e9,
                      "note": ef_note},
-        "roofline_hbm_kernel": {"kernel": "edge_msg_kernel<%d>" % wl["e"], "bound": "hbm", "achieved": msg_bytes / (msg_ms * 1e-3) / 1e9,
+        "roofline_hbm_kernel": {"kernel": "edge_msg_tc_kernel<%d>" % wl["e"], "bound": "hbm", "achieved": msg_bytes / (msg_ms * 1e-3) / 1e9,
                                 "peak": hbm, "unit": "GB/s", "frac": msg_bytes / (msg_ms * 1e-3) / 1e9 / hbm,
-                                "traffic": traffic_of("edge_msg_kernel<%d>" % wl["e"]), "algorithmic_bytes_per_launch": msg_bytes,
+                                "traffic": traffic_of("edge_msg_tc_kernel<%d>" % wl["e"]), "algorithmic_bytes_per_launch": msg_bytes,
                                 "ms_per_launch": msg_ms},
         "e2e": {"value": B * world / (ms_e2e / 1000.0), "unit": "graphs/s", "h2d_bytes_per_step": io["h2d"], "d2h_bytes_per_step": io["d2h"],
                 "ms_per_step": ms_e2e, "api": "gnn_motion_planning_b200.batch.HotPath.submit/wait (double-buffered; read-back of "

@@ -4,7 +4,8 @@
 //      per-thread values ptxas emits an ELECT / R2UR waterfall per MMA: ~62 cycles each regardless of N.)
 //   2. D = A.B^T with A in shared memory (SS) and in TMEM (TS), 1xTF32 and 3xTF32, error against fp64;
 //      tells whether operand conversion truncates and how close 3xTF32 gets to fp32;
-//   3. cycle counts: MMA group issue -> commit latency, tcgen05.ld / tcgen05.st throughput with 4 and 8 warps.
+//   3. cycle counts: MMA group issue -> commit latency, tcgen05.ld / tcgen05.st throughput with 4 and 8 warps;
+//   4. tcgen05.ld throughput by shape (32x32b / 16x256b / 16x128b): 57 B/cycle/SM in every case.
 // Results of the run this library was designed around: profiles/r1_umma_tf32_microbench.log.
 // Build + run on the GPU box:
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I gnn_motion_planning_b200/csrc \
@@ -195,8 +196,10 @@ void run_case(const char* name) {
 }
 
 int main2();
+int main4();
 int main() {
   main2();
+  main4();
   return 0;
   run_case<32, 32>("gemm");
   run_case<64, 32>("gemm");
@@ -282,5 +285,61 @@ int main2() {
   run_pattern<32>(dout);
   run_pattern<64>(dout);
   run_pattern<128>(dout);
+  return 0;
+}
+
+// ---- part 4: does the tcgen05.ld shape change the TMEM -> register bandwidth?  (4 KB per warp instruction in every case)
+template <int SHAPE>
+__global__ void __launch_bounds__(128) tmem_ld_shape(int iters, long long* out, float* sink) {
+  __shared__ uint32_t tmem_slot;
+  const int t = threadIdx.x, warp = t >> 5;
+  if (warp == 0) umma::tmem_alloc(&tmem_slot, 512);
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t base = tmem_slot + ((uint32_t)(warp * 32) << 16);
+  uint32_t r[32];
+  for (int i = 0; i < 32; ++i) r[i] = 0;
+  __syncthreads();
+  long long t0 = clock64();
+  uint32_t acc = 0;
+  for (int it = 0; it < iters; ++it) {
+    const uint32_t a = base + (it & 7) * 32;
+    if (SHAPE == 0) {
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                   : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]) : "r"(a) : "memory");
+    } else if (SHAPE == 1) {
+      asm volatile("tcgen05.ld.sync.aligned.16x256b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                   : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]) : "r"(a) : "memory");
+    } else {
+      asm volatile("tcgen05.ld.sync.aligned.16x128b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                   : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]) : "r"(a) : "memory");
+    }
+    umma::wait_ld();
+    acc += r[it & 31];
+  }
+  __syncthreads();
+  long long t1 = clock64();
+  if (t == 0) out[0] = t1 - t0;
+  sink[t] = (float)acc;
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem_slot, 512);
+}
+
+int main4() {
+  long long* dout; float* sink; long long h = 0;
+  cudaMalloc(&dout, 16); cudaMalloc(&sink, 256 * 4);
+  const int iters = 4096;
+  const char* names[3] = {"32x32b.x32", "16x256b.x8", "16x128b.x16"};
+  for (int sh = 0; sh < 3; ++sh) {
+    if (sh == 0) tmem_ld_shape<0><<<1, 128>>>(iters, dout, sink);
+    if (sh == 1) tmem_ld_shape<1><<<1, 128>>>(iters, dout, sink);
+    if (sh == 2) tmem_ld_shape<2><<<1, 128>>>(iters, dout, sink);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("tmem_ld_shape %s: CUDA error %s\n", names[sh], cudaGetErrorString(e)); return 1; }
+    cudaMemcpy(&h, dout, 8, cudaMemcpyDeviceToHost);
+    printf("tcgen05.ld.%s, 4 warps: %.1f cyc per 16 KB (%.1f B/cyc/SM)\n", names[sh], (double)h / iters, (double)iters * 128 * 32 * 4 / h);
+  }
   return 0;
 }

@@ -5,7 +5,10 @@
 //   2. D = A.B^T with A in shared memory (SS) and in TMEM (TS), 1xTF32 and 3xTF32, error against fp64;
 //      tells whether operand conversion truncates and how close 3xTF32 gets to fp32;
 //   3. cycle counts: MMA group issue -> commit latency, tcgen05.ld / tcgen05.st throughput with 4 and 8 warps;
-//   4. tcgen05.ld throughput by shape (32x32b / 16x256b / 16x128b): 57 B/cycle/SM in every case.
+//   4. tcgen05.ld throughput by shape: 32x32b.x32 ~410 B/cycle/SM, 16x256b.x8 ~190, 16x128b.x16 ~290 (one load in flight per warp);
+//   5. four loads in flight per warp: 550 (4 warps) - 850 (8 warps) B/cycle/SM.
+// Lesson kept in the code: index the destination arrays of tcgen05.ld with compile-time constants only -- a dynamic index moves the
+// array to local memory and the loop then times the spills (an early version of part 3 reported 57 B/cycle that way).
 // Results of the run this library was designed around: profiles/r1_umma_tf32_microbench.log.
 // Build + run on the GPU box:
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I gnn_motion_planning_b200/csrc \
@@ -134,12 +137,12 @@ __global__ void __launch_bounds__(256) tmem_bw(int iters, long long* out, float*
   for (int it = 0; it < iters; ++it) {
     umma::ld32(base + (it & 7) * 32, r);
     umma::wait_ld();
-    acc += r[it & 31];
+    acc += r[0] + r[31];   // static indices: a dynamic index would push r[] to local memory and time the spills instead
   }
   __syncthreads();
   long long t1 = clock64();
   for (int it = 0; it < iters; ++it) {
-    r[it & 31] += 1.0f;
+    r[0] += 1.0f;
     umma::st32(base + (it & 7) * 32, r);
   }
   umma::wait_st();
@@ -197,9 +200,11 @@ void run_case(const char* name) {
 
 int main2();
 int main4();
+int main5();
 int main() {
   main2();
   main4();
+  main5();
   return 0;
   run_case<32, 32>("gemm");
   run_case<64, 32>("gemm");
@@ -316,7 +321,7 @@ __global__ void __launch_bounds__(128) tmem_ld_shape(int iters, long long* out, 
                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]) : "r"(a) : "memory");
     }
     umma::wait_ld();
-    acc += r[it & 31];
+    acc += r[0] + r[31];   // static indices (see part 5)
   }
   __syncthreads();
   long long t1 = clock64();
@@ -340,6 +345,48 @@ int main4() {
     if (e != cudaSuccess) { printf("tmem_ld_shape %s: CUDA error %s\n", names[sh], cudaGetErrorString(e)); return 1; }
     cudaMemcpy(&h, dout, 8, cudaMemcpyDeviceToHost);
     printf("tcgen05.ld.%s, 4 warps: %.1f cyc per 16 KB (%.1f B/cyc/SM)\n", names[sh], (double)h / iters, (double)iters * 128 * 32 * 4 / h);
+  }
+  return 0;
+}
+
+// ---- part 5: four tcgen05.ld (32x32b.x32) in flight per warp before one wait
+__global__ void __launch_bounds__(256) tmem_ld_depth(int iters, long long* out, float* sink) {
+  __shared__ uint32_t tmem_slot;
+  const int t = threadIdx.x, warp = t >> 5;
+  if (warp == 0) umma::tmem_alloc(&tmem_slot, 512);
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t base = tmem_slot + ((uint32_t)((warp & 3) * 32) << 16) + (warp >> 2) * 256;
+  float r0[32], r1[32], r2[32], r3[32];
+  __syncthreads();
+  long long t0 = clock64();
+  float acc = 0.f;
+  for (int it = 0; it < iters; ++it) {
+    umma::ld32(base, r0); umma::ld32(base + 32, r1); umma::ld32(base + 64, r2); umma::ld32(base + 96, r3);
+    umma::wait_ld();
+    acc += r0[0] + r1[7] + r2[19] + r3[31];   // static indices: a dynamic index would push the arrays to local memory
+  }
+  __syncthreads();
+  long long t1 = clock64();
+  if (t == 0) out[0] = t1 - t0;
+  sink[t] = acc;
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem_slot, 512);
+}
+
+int main5() {
+  long long* dout; float* sink; long long h = 0;
+  cudaMalloc(&dout, 16); cudaMalloc(&sink, 256 * 4);
+  const int iters = 2048;
+  for (int threads : {128, 256}) {
+    tmem_ld_depth<<<1, threads>>>(iters, dout, sink);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("tmem_ld_depth: CUDA error %s\n", cudaGetErrorString(e)); return 1; }
+    cudaMemcpy(&h, dout, 8, cudaMemcpyDeviceToHost);
+    printf("tcgen05.ld x4 in flight, %d threads: %.1f cyc per iteration (%.1f B/cyc/SM)\n", threads, (double)h / iters,
+           (double)iters * threads * 128 * 4 / h);
   }
   return 0;
 }

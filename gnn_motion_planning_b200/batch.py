@@ -11,7 +11,9 @@
 ``compute`` runs one batch from device-resident inputs.  ``submit`` / ``wait`` are the end-to-end path: inputs come
 from pinned host buffers, results (edge_index, logits, free flags, edge_ptr) are delivered into pinned host buffers;
 two device/host buffer sets and three streams (graph build | forward + collision | read-back) keep the GPU busy
-across batches.
+across batches.  The edge list travels back as LOCAL ids in int16 (int32 when a graph has more than 32 767 nodes):
+4 B/edge instead of the 16 B/edge of the int64 ``[2,E]`` PyG layout, which was 76 % of the read-back (the int64 tensor
+stays on the device for the kernels; ``result["edge_index"].to(torch.int64)`` restores the reference dtype on the host).
 """
 import numpy as np
 import torch
@@ -32,6 +34,7 @@ class HotPath:
         self.k1 = np.full(self.B, self.k, np.int32)
         self.maps, self.boxes, self.box_ptr, self.arm_model, self.rrt_eps = maps, boxes, box_ptr, arm_model, rrt_eps
         self.cap = int(self.B * _lib.load().gmp_knn_graph_max_edges(self.N, self.k))
+        self.id_dtype = torch.int16 if self.N <= 32767 else torch.int32
         self.sets = [self._alloc_set() for _ in range(2)]
         self.copy_stream = torch.cuda.Stream(device=self.dev)
         self.graph_stream = torch.cuda.Stream(device=self.dev)
@@ -42,6 +45,7 @@ class HotPath:
         s = dict(ei=torch.empty((2, self.cap), dtype=torch.int64, device=d), logits=torch.empty(self.cap, dtype=torch.float32, device=d),
                  free=torch.empty(self.cap, dtype=torch.uint8, device=d), checks=torch.empty(self.cap, dtype=torch.int32, device=d),
                  rows=torch.empty((self.B, 4), dtype=torch.float32, device=d),
+                 ei_narrow=torch.empty((2, self.cap), dtype=self.id_dtype, device=d), pending=None,
                  compute_done=torch.cuda.Event(), copy_done=torch.cuda.Event(), et=0, edge_ptr=None, host=None, inputs=None)
         return s
 
@@ -86,7 +90,7 @@ class HotPath:
     # ------------------------------------------------------------------ end to end: pinned host in, pinned host out
     def _host_set(self):
         pin = lambda *shape, dtype: torch.empty(*shape, dtype=dtype).pin_memory()  # noqa: E731
-        return dict(ei=pin((2, self.cap), dtype=torch.int64), logits=pin(self.cap, dtype=torch.float32),
+        return dict(ei=pin((2, self.cap), dtype=self.id_dtype), logits=pin(self.cap, dtype=torch.float32),
                     free=pin(self.cap, dtype=torch.uint8), rows=pin((self.B, 4), dtype=torch.float32))
 
     def submit(self, v_h, goal_h, obs_h, obs_ptr, prob_h, maps_h=None):
@@ -96,6 +100,10 @@ class HotPath:
         The only host synchronisation is the B+1-int edge_ptr read-back of the graph build, which waits for the graph
         stream only -- the main stream never drains."""
         s = self.sets[self._k % 2]
+        if s["pending"] is not None:
+            raise RuntimeError("HotPath.submit: at most two batches may be in flight -- wait() on the ticket of batch %d first "
+                               "(its host buffers would be overwritten)" % s["pending"])
+        s["pending"] = self._k
         self._k += 1
         if s["host"] is None:
             s["host"] = self._host_set()
@@ -120,24 +128,31 @@ class HotPath:
             s["graph_done"].record(gs)
         main.wait_event(s["graph_done"])
         self._score_and_check(staged[0], staged[1], staged[2], obs_ptr, staged[3], s, maps=s["maps_d"])
-        s["compute_done"].record(main)
         n = s["et"]
+        _lib.check(_lib.load().gmp_edge_index_narrow(_lib.ptr(s["ei"]), s["ei"].stride(0), n, 16 if self.id_dtype == torch.int16 else 32,
+                                                     _lib.ptr(s["ei_narrow"]), s["ei_narrow"].stride(0), _lib.stream_ptr(self.dev)))
+        s["compute_done"].record(main)
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(s["compute_done"])
             s["host"]["logits"][:n].copy_(s["logits"][:n], non_blocking=True)
             s["host"]["free"][:n].copy_(s["free"][:n], non_blocking=True)
-            s["host"]["ei"][0, :n].copy_(s["ei"][0, :n], non_blocking=True)
-            s["host"]["ei"][1, :n].copy_(s["ei"][1, :n], non_blocking=True)
+            s["host"]["ei"][0, :n].copy_(s["ei_narrow"][0, :n], non_blocking=True)
+            s["host"]["ei"][1, :n].copy_(s["ei_narrow"][1, :n], non_blocking=True)
             s["host"]["rows"].copy_(s["rows"], non_blocking=True)
             s["copy_done"].record(self.copy_stream)
         s["h2d_bytes"] = sum(t.numel() * t.element_size() for t in (v_h, goal_h, obs_h, prob_h) + ((maps_h,) if maps_h is not None else ()))
-        s["d2h_bytes"] = n * (4 + 1 + 16) + self.B * 16 + (self.B + 1) * 4
-        return s
+        s["d2h_bytes"] = n * (4 + 1 + 2 * s["host"]["ei"].element_size()) + self.B * 16 + (self.B + 1) * 4
+        # the ticket snapshots what belongs to THIS batch; the buffer set itself is reused two submits later
+        return dict(set=s, seq=s["pending"], et=n, edge_ptr=s["edge_ptr"], rows=s["rows"], h2d_bytes=s["h2d_bytes"], d2h_bytes=s["d2h_bytes"])
 
     @staticmethod
     def wait(ticket):
         """Block until the results of a submitted batch are in its pinned host buffers; returns them."""
-        ticket["copy_done"].synchronize()
+        s = ticket["set"]
+        if s["pending"] != ticket["seq"]:
+            raise RuntimeError("HotPath.wait: this ticket's buffers were already waited on and reused")
+        s["copy_done"].synchronize()
+        s["pending"] = None
         n = ticket["et"]
-        h = ticket["host"]
+        h = s["host"]
         return dict(edge_ptr=ticket["edge_ptr"], edge_index=h["ei"][:, :n], logits=h["logits"][:n], free=h["free"][:n], rows=h["rows"])

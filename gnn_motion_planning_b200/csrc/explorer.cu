@@ -1370,7 +1370,8 @@ int run_forward(gmp_handle* h, int64_t B, const float* v, const int64_t* edge_in
 
   const size_t smem = Smem<E, true>::kBytes;     // node / obstacle kernels (two activation buffers)
   const size_t smem1 = Smem<E, false>::kBytes;   // per-edge kernels (one activation buffer)
-  static bool attr_done = false;
+  // per handle, not per process: cudaFuncSetAttribute is per DEVICE, and a process may hold handles on several GPUs
+  bool& attr_done = h->ex_attr_done;
   if (!attr_done) {
     GMP_CUDA(cudaFuncSetAttribute(obstacle_kernel<S, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     GMP_CUDA(cudaFuncSetAttribute(node_pre_kernel<C, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1489,7 +1490,7 @@ int run_forward(gmp_handle* h, int64_t B, const float* v, const int64_t* edge_in
   }
   tl.end(st);
   const int node_tiles = (int)((Nt + R - 1) / R), slot_tiles = (int)((Et + R - 1) / R);
-  static int msg_grid = 0;   // persistent grid of the message kernel: every resident CTA slot of the device
+  int& msg_grid = h->ex_msg_grid;   // persistent grid of the message kernel: every resident CTA slot of the device
   if (msg_grid == 0) {
     int per_sm = 0;
     GMP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, edge_msg_kernel<E>, kRtThreads, MsgSmem<E>::kBytes));
@@ -1567,6 +1568,8 @@ extern "C" int gmp_explorer_init(gmp_handle* h, int config_size, int embed_size,
   GMP_REQUIRE(obs_size == 2 || obs_size == 6, "obs_size must be 2 or 6");
   h->ex.c = config_size; h->ex.e = embed_size; h->ex.s = obs_size;
   h->ex.ready = false;
+  h->ex_attr_done = false;   // another (c, e, s) means other kernel instantiations
+  h->ex_msg_grid = 0;
   h->ex.tensors.clear();
   return GMP_OK;
 }

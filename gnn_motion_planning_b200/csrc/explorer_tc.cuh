@@ -646,7 +646,7 @@ struct MsgTc {
   // 32 consecutive floats -- every access conflict-free, a quarter of the LSU instructions of a feature-major tile
   static constexpr int kX = R * XP;
   static constexpr int kW = 2 * E * E + 2 * E;   // lin_0[2] / policy[2]: hi plane | lo plane | bias | (policy[4] weight)
-  static constexpr size_t kNeed = (size_t)(kPS + kX + kW) * sizeof(float) + 2 * R * sizeof(int);
+  static constexpr size_t kNeed = (size_t)(kPS + kX + kW) * sizeof(float) + 4 * R * sizeof(int);   // IDX / SRC double-buffered
   // tensor memory: XH | XL | D = 3E columns, allocated as a power of two; kCtas CTAs per SM share the 512 columns.  The
   // shared-memory request is padded so that exactly kCtas fit: one more could not allocate tensor memory and would stall
   static constexpr int kTmemCols = E == 32 ? 128 : 256;
@@ -678,8 +678,10 @@ __global__ void __launch_bounds__(128, MsgTc<E_>::kCtas) edge_msg_tc_kernel(cons
   float* PS = smem_msg;                       // first: 128 B aligned for the bulk copy
   float* X = PS + M::kPS;
   float* WB = X + M::kX;
-  int* IDX = reinterpret_cast<int*>(WB + M::kW);
-  int* SRC = IDX + R;
+  // target / source ids of the tile, DOUBLE-BUFFERED by tile parity: for E = 64 the segmented-max scan of a warp reads the ids
+  // of rows another warp owns, and the next tile's ids are stored before the loop-top barrier -- with one buffer a fast warp
+  // would overwrite ids a slow warp is still scanning.  With two, a buffer is rewritten only two barriers later.
+  int* IDX2 = reinterpret_cast<int*>(WB + M::kW);
   __shared__ uint64_t bar_p, bar_mma;
   __shared__ uint32_t tmem_slot;
   const int warp_u = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
@@ -715,7 +717,9 @@ __global__ void __launch_bounds__(128, MsgTc<E_>::kCtas) edge_msg_tc_kernel(cons
     ndst = ok ? __ldg(csr_dst + slot) : -1;
   };
   load_indices(tile);
-  for (; tile < n_tiles; tile += gridDim.x) {
+  for (int par = 0; tile < n_tiles; tile += gridDim.x, par ^= 1) {
+    int* IDX = IDX2 + par * 2 * R;
+    int* SRC = IDX + R;
     SRC[threadIdx.x] = nsrc;
     IDX[threadIdx.x] = ndst;
     __syncthreads();           // indices visible; X free (previous scan done)
@@ -844,7 +848,7 @@ __global__ void __launch_bounds__(128, MsgTc<E_>::kCtas) edge_msg_tc_kernel(cons
       }
     }
     if (cur >= 0) atomic_max_f32(AGG + (size_t)cur * E + n, run);
-    // (the loop-top barrier protects IDX / X; tensor memory is rewritten only after the next tile's barriers)
+    // (the loop-top barrier protects X, the parity buffers protect IDX; tensor memory is rewritten only after the next tile's barriers)
   }
   umma::fence_before_sync();
   __syncthreads();

@@ -112,4 +112,7 @@ struct gmp_handle {
   gmp::ExplorerModel ex;
   gmp::SmootherModel sm;
   gmp::Timeline tl;
+  // launch state of the explorer kernels on THIS handle's device (shared-memory opt-in done, persistent grid size)
+  bool ex_attr_done = false;
+  int ex_msg_grid = 0;
 };

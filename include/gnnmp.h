@@ -198,6 +198,12 @@ int gmp_smoother_forward(gmp_handle* h, int64_t n_problems, const float* path, c
 int gmp_result_rows(const float* edge_logits, const uint8_t* edge_free, const int32_t* edge_ptr, int64_t n_graphs,
                     int32_t first_problem_id, float* rows_out, void* stream);
 
+/* Local node ids of a packed edge_index as int16 (bits = 16: every N_g <= 32767) or int32 (bits = 32) for the
+ * device->host read-back of the batched path: 4 B/edge instead of the 16 B/edge of torch_geometric's int64 layout
+ * (eval_gnn.py:164).  out [2, out_row_stride] of that type. */
+int gmp_edge_index_narrow(const int64_t* edge_index, int64_t edge_row_stride, int64_t n_edges, int bits, void* out,
+                          int64_t out_row_stride, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -295,5 +295,163 @@ def main():
     np.savez_compressed(os.path.join(HERE, "explore_c1.npz"), **e2e)
 
 
+def more_goldens():
+    """Round-2 fixtures: every (config, embed, obs) combination of reference str2name.py:12-66 that round 1 left
+    uncovered, the remaining shipped smoother weights, and the a5 row (smoother.py:194-246 run for real).
+    Own RNGs, own files: the round-1 fixtures above stay bit-identical."""
+    os.chdir(REF)
+    sys.path.insert(0, REF)
+    MazeEnv = load_ref_maze_env()
+    import model as ref_model
+    import model_smoother as ref_model_smoother
+    wdir = os.path.join(HERE, "weights")
+    os.makedirs(wdir, exist_ok=True)
+    for w in ("weights_kuka_13.pt", "weights_maze_3.pt", "smooth_13d_attv3.pt", "smooth_14d_attv3.pt",
+              "smooth_snake_attv3.pt", "smooth_ur5_attv3.pt"):
+        shutil.copyfile(os.path.join(REF, "data/weights", w), os.path.join(wdir, w))
+    env = MazeEnv(dim=2)
+    rng = np.random.default_rng(20261017)
+
+    # ---------------------------------------------------------------- explorer (model.py:115-150): snake7, ur5, kuka13, maze3
+    ex = {}
+    cfgs = {
+        "snake7": dict(w="weights_snake.pt", c=7, e=32, s=2, ws=3, n=180, k=9, lo=-1.0, hi=1.0),
+        "ur5": dict(w="weights_ur5.pt", c=6, e=32, s=6, ws=3, n=170, k=8, lo=-3.1, hi=3.1),
+        "kuka13": dict(w="weights_kuka_13.pt", c=13, e=32, s=6, ws=3, n=150, k=8, lo=-2.0, hi=2.0),
+        "maze3": dict(w="weights_maze_3.pt", c=3, e=32, s=2, ws=2, n=160, k=8, lo=-1.0, hi=1.0),
+    }
+    for tag, cf in cfgs.items():
+        m = ref_model.EncoderProcessDecoder(workspace_size=cf["ws"], config_size=cf["c"], embed_size=cf["e"],
+                                            obs_size=cf["s"])
+        m.load_state_dict(torch.load(os.path.join(REF, "data/weights", cf["w"]), map_location="cpu"))
+        m.eval()
+        v = torch.from_numpy(rng.uniform(cf["lo"], cf["hi"], (cf["n"], cf["c"])).astype(np.float32))
+        ei = sym_knn_edges(v, cf["k"])
+        if cf["s"] == 2:                                               # occupied cells of a real map (maze_env.py:73-79)
+            env.init_new_problem(2001 if tag == "snake7" else 2003)
+            obs = torch.FloatTensor(env.obstacles)
+        else:                                                          # boxes (half extents, position), 2..12 of them
+            nb = 12 if tag == "ur5" else 7
+            obs = torch.from_numpy(np.concatenate([rng.uniform(0.05, 0.3, (nb, 1, 3)),
+                                                   rng.uniform(-0.8, 0.8, (nb, 1, 3))], 1).astype(np.float32))
+        for loop in (1, 5):
+            with torch.no_grad():
+                dense = m(goal=v[1], loop=loop, v=v, obstacles=obs, free=None, collided=None, edge_index=ei, labels=None)
+            ex["%s_logits_loop%d" % (tag, loop)] = dense[ei[1], ei[0]].numpy()
+        m.use_obstacles = False
+        with torch.no_grad():
+            dense = m(goal=v[1], loop=5, v=v, obstacles=obs, free=None, collided=None, edge_index=ei)
+        ex[tag + "_logits_noobs"] = dense[ei[1], ei[0]].numpy()
+        ex.update({tag + "_v": v.numpy(), tag + "_edge_index": ei.numpy(), tag + "_obstacles": obs.numpy(),
+                   tag + "_goal": v[1].numpy()})
+        print("explorer", tag, tuple(ei.shape), float(ex[tag + "_logits_loop5"].mean()), float(ex[tag + "_logits_loop5"].std()))
+    np.savez_compressed(os.path.join(HERE, "explorer_more.npz"), **ex)
+
+    # ---------------------------------------------------------------- smoother (model_smoother.py:104-142): 14d, 13d, ur5, snake
+    sm = {}
+    UR5_SCALE = 6.28318530718       # np.max(env.bound) of UR5Env = the largest joint limit of ur5/ur5.urdf:38 (str2name.py:40)
+    for tag, (w, c, p, nf, ncol, scale, lo, hi) in {
+            "14d": ("smooth_14d_attv3.pt", 14, 11, 80, 50, 1.0, -2.9, 2.9),
+            "13d": ("smooth_13d_attv3.pt", 13, 8, 60, 60, 1.0, -2.0, 2.0),
+            "ur5": ("smooth_ur5_attv3.pt", 6, 13, 90, 30, UR5_SCALE, -6.2, 6.2),
+            "snake": ("smooth_snake_attv3.pt", 7, 10, 70, 45, 1.0, -1.0, 1.0)}.items():
+        ms = ref_model_smoother.ModelSmoother(workspace_size=3, config_size=c, embed_size=128, obs_size=6, scale=scale)
+        ms.load_state_dict(torch.load(os.path.join(REF, "data/weights", w), map_location="cpu"))
+        ms.eval()
+        step = (hi - lo) / 25
+        path = torch.from_numpy(np.cumsum(rng.uniform(-step, 1.5 * step, (p, c)), 0).astype(np.float32)).clamp(lo, hi)
+        free = torch.from_numpy(rng.uniform(lo, hi, (nf, c)).astype(np.float32))
+        coll = torch.from_numpy(rng.uniform(lo, hi, (ncol, c)).astype(np.float32))
+        e = torch.cat((torch.arange(1, p).reshape(1, -1), torch.arange(0, p - 1).reshape(1, -1)), 0)
+        e = torch.cat((e, e.flip(0)), -1)
+        e, _ = _pyg_stubs.add_self_loops(e, num_nodes=p)
+        for loop in (1, 3):
+            with torch.no_grad():
+                newp = ms(path=path.clone(), free=free, collided=coll, obstacles=None, edge_index=e, loop=loop)
+            sm["%s_out_loop%d" % (tag, loop)] = newp.numpy()
+        sm.update({tag + "_path": path.numpy(), tag + "_free": free.numpy(), tag + "_collided": coll.numpy(),
+                   tag + "_edge_index": e.numpy(), tag + "_scale": np.array(scale)})
+        print("smoother", tag, tuple(newp.shape), float(np.abs(newp.numpy() - path.numpy()).max()))
+    np.savez_compressed(os.path.join(HERE, "smoother_more.npz"), **sm)
+
+    # ---------------------------------------------------------------- a5: model_smooth / proposed_path_smootherv2 (smoother.py:194-246)
+    # The reference's own steering loop + smoother model + MazeEnv, on paths found by the reference's own explore().
+    import time as _time
+    from copy import deepcopy
+    dot = type("DotDict", (dict,), dict(__getattr__=dict.get, __setattr__=dict.__setitem__))
+    ns_s = dict(torch=torch, np=np, deepcopy=deepcopy, device=torch.device("cpu"), DotDict=dot,
+                add_self_loops=_pyg_stubs.add_self_loops)
+    ref_functions("smoother.py", ["obs_data", "proposed_path_smootherv2", "model_smooth"], ns_s)
+    ns = dict(torch=torch, np=np, Data=_pyg_stubs.Data, knn_graph=_pyg_stubs.knn_graph, coalesce=_pyg_stubs.coalesce,
+              time=_time.time, device=torch.device("cpu"), loop=5, DotDict=dot, model_smooth=ns_s["model_smooth"])
+    ref_functions("eval_gnn.py", ["create_data", "explore", "obs_data", "to_np", "path_cost"], ns)
+    m = ref_model.EncoderProcessDecoder(workspace_size=2, config_size=2, embed_size=32, obs_size=2)
+    m.load_state_dict(torch.load(os.path.join(REF, "data/weights/weights_maze.pt"), map_location="cpu"))
+    m.eval()
+    ms = ref_model_smoother.ModelSmoother(workspace_size=2, config_size=2, embed_size=128, obs_size=6)
+    ms.load_state_dict(torch.load(os.path.join(REF, "data/weights/smooth_2d_attv3.pt"), map_location="cpu"))
+    ms.eval()
+
+    class LegacyIndexTensor(torch.Tensor):     # eval_gnn.py:202 under the author's torch (see main())
+        def __setitem__(self, idx, val):
+            if isinstance(idx, np.ndarray) and idx.ndim == 2 and idx.shape[0] < 32:
+                idx = tuple(torch.from_numpy(r) for r in idx)
+            return super().__setitem__(idx, val)
+    ref_forward = m.forward
+    m.forward = lambda *a, **k: ref_forward(*a, **k).as_subclass(LegacyIndexTensor)
+
+    # record every model_smooth call the reference makes (inputs, output, collision-check delta) ...
+    calls = []
+    ref_model_smooth = ns_s["model_smooth"]
+
+    def recording_model_smooth(model, free, collided, old_path, env_, iter=5):
+        rec = dict(free=np.array(free), collided=np.array(collided) if len(collided) else np.zeros((0, 2)),
+                   path=np.array(old_path), c0=env_.collision_check_count)
+        out = ref_model_smooth(model, free, collided, old_path, env_, iter=iter)
+        rec["out"] = np.array(out)
+        rec["checks"] = env_.collision_check_count - rec["c0"]
+        calls.append(rec)
+        return out
+    ns["model_smooth"] = recording_model_smooth
+    # ... and every steering call inside it
+    steer = []
+    ref_steer = ns_s["proposed_path_smootherv2"]
+
+    def recording_steer(old_path, new_path, env_):
+        c0 = env_.collision_check_count
+        out = ref_steer(old_path, new_path, env_)
+        steer.append(dict(old=np.array(old_path), new=np.array(new_path), out=np.array(out),
+                          checks=env_.collision_check_count - c0, old_dtype=str(np.array(old_path[1]).dtype)))
+        return out
+    ns_s["proposed_path_smootherv2"] = recording_steer
+
+    a5 = {}
+    ids = [2000, 2001, 2002, 2003, 2004, 2005]
+    for pid in ids:
+        np.random.seed(4321 + pid)
+        env.init_new_problem(pid)
+        n_before, s_before = len(calls), len(steer)
+        r = ns["explore"](env, m, ms, smooth=True, batch=100, t_max=100, k=10, smoother="model")
+        a5["p%d_success" % pid] = np.array(r["success"])
+        a5["p%d_c_explore" % pid] = np.array(r["c_explore"])
+        a5["p%d_c_smooth" % pid] = np.array(r["c_smooth"])
+        a5["p%d_path" % pid] = np.array(r["path"])
+        a5["p%d_smooth_path" % pid] = np.array(r["smooth_path"])
+        if len(calls) > n_before:
+            c = calls[-1]
+            a5.update({"p%d_ms_free" % pid: c["free"], "p%d_ms_collided" % pid: c["collided"], "p%d_ms_path" % pid: c["path"],
+                       "p%d_ms_out" % pid: c["out"], "p%d_ms_checks" % pid: np.array(c["checks"])})
+            for j, st in enumerate(steer[s_before:]):
+                a5.update({"p%d_steer%d_old" % (pid, j): st["old"], "p%d_steer%d_new" % (pid, j): st["new"],
+                           "p%d_steer%d_out" % (pid, j): st["out"], "p%d_steer%d_checks" % (pid, j): np.array(st["checks"])})
+            a5["p%d_n_steer" % pid] = np.array(len(steer) - s_before)
+        print("a5 explore+smooth", pid, r["success"], r["c_explore"], r["c_smooth"], len(r["path"]),
+              "cost %.4f -> %.4f" % (ns["path_cost"](r["path"]), ns["path_cost"](r["smooth_path"])) if r["success"] else "")
+    a5["ids"] = np.array(ids)
+    np.savez_compressed(os.path.join(HERE, "model_smooth.npz"), **a5)
+
+
 if __name__ == "__main__":
-    main()
+    if "--more-only" not in sys.argv:
+        main()
+    more_goldens()

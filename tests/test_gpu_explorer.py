@@ -9,8 +9,17 @@ pytestmark = pytest.mark.gpu
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 TOL = 1e-4  # BASELINE.json north_star: "edge logits within 1e-4 fp32"
 
+# all seven (config, embed, obs) combinations of reference str2name.py:12-66 == model.SUPPORTED_DIMS
 CASES = [("maze2", "weights_maze.pt", (2, 2, 32, 2)), ("kuka7", "weights_kuka.pt", (3, 7, 64, 6)),
-         ("kuka14", "kuka_14.pt", (3, 14, 32, 6))]
+         ("kuka14", "kuka_14.pt", (3, 14, 32, 6)), ("snake7", "weights_snake.pt", (3, 7, 32, 2)),
+         ("ur5", "weights_ur5.pt", (3, 6, 32, 6)), ("kuka13", "weights_kuka_13.pt", (3, 13, 32, 6)),
+         ("maze3", "weights_maze_3.pt", (2, 3, 32, 2))]
+MORE = ("snake7", "ur5", "kuka13", "maze3")          # fixtures of round 2: tests/golden/explorer_more.npz
+
+
+def test_cases_cover_every_supported_instantiation():
+    from gnn_motion_planning_b200.model import SUPPORTED_DIMS
+    assert {(d[1], d[2], d[3]) for _, _, d in CASES} == set(SUPPORTED_DIMS)
 
 
 def make_model(wfile, dims, dev):
@@ -22,7 +31,7 @@ def make_model(wfile, dims, dev):
 
 @pytest.mark.parametrize("tag,wfile,dims", CASES)
 def test_forward_golden(cuda_device, tag, wfile, dims):
-    ex = np.load(os.path.join(G, "explorer.npz"))
+    ex = np.load(os.path.join(G, "explorer_more.npz" if tag in MORE else "explorer.npz"))
     m = make_model(wfile, dims, cuda_device)
     v = torch.from_numpy(ex[tag + "_v"]).to(cuda_device)
     ei = torch.from_numpy(ex[tag + "_edge_index"]).to(cuda_device)

@@ -131,8 +131,62 @@ def test_hotpath_submit_wait_matches_compute(cuda_device):
         if it == 1:   # results of an older batch stay valid while newer ones are in flight (two buffer sets)
             r0 = HotPath.wait(tickets[0])
             assert torch.equal(r0["logits"], wants[0][2])
+    with pytest.raises(RuntimeError):                                     # the ticket of batch 0 was consumed: its buffers are reused
+        HotPath.wait(tickets[0])
     for t, (ep, ei, lg, fr, rows) in list(zip(tickets, wants))[1:]:
         r = HotPath.wait(t)
-        assert np.array_equal(r["edge_ptr"], ep) and torch.equal(r["edge_index"], ei)
+        assert r["edge_index"].dtype == torch.int16                       # local ids travel narrow (N <= 32767): 4 B/edge, not 16
+        assert np.array_equal(r["edge_ptr"], ep) and torch.equal(r["edge_index"].to(torch.int64), ei)
         assert torch.equal(r["logits"], lg) and torch.equal(r["free"], fr) and torch.equal(r["rows"], rows)
         assert float(rows[0, 0]) == 40.0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# BASELINE configs[2] / configs[3] sizes: ONE graph of each against the oracle at the 1e-4 gate
+KUKA_LIM = np.array([2.967, 2.094, 2.967, 2.094, 2.967, 2.094, 3.054])      # kuka_iiwa/model_0.urdf joint limits
+
+
+def _one_graph_vs_oracle(dev, wfile, dims, n, k, lim, boxes, seed):
+    from gnn_motion_planning_b200 import graph
+    from gnn_motion_planning_b200.model import EncoderProcessDecoder
+    from oracle import explorer as o_explorer
+    from oracle import knn_graph as o_knn
+    sd = torch.load(os.path.join(G, "weights", wfile), map_location="cpu")
+    m = EncoderProcessDecoder(*dims).to(dev)
+    m.load_state_dict(sd)
+    rng = np.random.default_rng(seed)
+    v = rng.uniform(-lim, lim, (n, len(lim))).astype(np.float32)
+    ei_want = o_knn.knn_graph_edges(v, n, k)
+    vd = torch.from_numpy(v).to(dev)
+    ei = graph.knn_graph_edges(vd, n, k)
+    assert np.array_equal(ei.cpu().numpy(), ei_want)                               # bit-exact edge indices at full size
+    obs = torch.from_numpy(boxes.astype(np.float32))
+    got = {}
+    for mode in ("tc", "simt"):
+        m.set_edge_feature_mode(mode)
+        got[mode] = m.forward_sparse(goal=vd[1], loop=5, v=vd, obstacles=obs.to(dev), edge_index=ei).cpu()
+    want = o_explorer.explorer_forward(sd, torch.from_numpy(v), torch.from_numpy(ei_want), torch.from_numpy(v[1]), obs, loop=5,
+                                       dense=False)
+    for mode in ("tc", "simt"):
+        err = float((got[mode] - want).abs().max())
+        assert err < 1e-4, (mode, err)
+    return ei_want, got
+
+
+def test_c3_size_graph_vs_oracle(cuda_device):
+    """C3: kuka7, embed 64 (phase-split tcgen05 stage), N=1000, k=50, the boxes of a real kukas_7 problem."""
+    arm = np.load(os.path.join(G, "arm_problems.npz"))
+    bp = arm["kuka7_box_ptr"]
+    g = int(np.argmax(np.diff(bp)))                                                # the problem with the most boxes
+    ei, _ = _one_graph_vs_oracle(cuda_device, "weights_kuka.pt", (3, 7, 64, 6), 1000, 50, KUKA_LIM,
+                                 arm["kuka7_boxes"][bp[g]:bp[g + 1]], 1234)
+    assert ei.shape[1] > 55000
+
+
+def test_c4_size_graph_vs_oracle(cuda_device):
+    """C4: kuka14, N=2000, k=50: hub rows (in-degree > 200) go through the segmented max of the message kernel."""
+    arm = np.load(os.path.join(G, "arm_problems.npz"))
+    bp = arm["kuka14_box_ptr"]
+    ei, _ = _one_graph_vs_oracle(cuda_device, "kuka_14.pt", (3, 14, 32, 6), 2000, 50, np.concatenate([KUKA_LIM, KUKA_LIM]),
+                                 arm["kuka14_boxes"][bp[3]:bp[4]], 1234)
+    assert ei.shape[1] > 120000 and int(np.bincount(ei[1]).max()) > 200

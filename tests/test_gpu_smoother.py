@@ -9,7 +9,10 @@ pytestmark = pytest.mark.gpu
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 TOL = 1e-4
 
-CASES = [("2d", "smooth_2d_attv3.pt", 2), ("7d", "smooth_7d_attv3.pt", 7), ("2d_short", "smooth_2d_attv3.pt", 2)]
+CASES = [("2d", "smooth_2d_attv3.pt", 2), ("7d", "smooth_7d_attv3.pt", 7), ("2d_short", "smooth_2d_attv3.pt", 2),
+         ("14d", "smooth_14d_attv3.pt", 14), ("13d", "smooth_13d_attv3.pt", 13), ("ur5", "smooth_ur5_attv3.pt", 6),
+         ("snake", "smooth_snake_attv3.pt", 7)]
+MORE = ("14d", "13d", "ur5", "snake")                # fixtures of round 2: tests/golden/smoother_more.npz (ur5: scale = 2*pi)
 
 
 def make(wfile, c, dev, scale=1.0):
@@ -21,8 +24,8 @@ def make(wfile, c, dev, scale=1.0):
 
 @pytest.mark.parametrize("tag,wfile,c", CASES)
 def test_forward_golden(cuda_device, tag, wfile, c):
-    sm = np.load(os.path.join(G, "smoother.npz"))
-    m = make(wfile, c, cuda_device)
+    sm = np.load(os.path.join(G, "smoother_more.npz" if tag in MORE else "smoother.npz"))
+    m = make(wfile, c, cuda_device, scale=float(sm[tag + "_scale"]) if tag in MORE else 1.0)
     path = torch.from_numpy(sm[tag + "_path"]).to(cuda_device)
     keep = path.clone()
     for loop in (1, 3):
@@ -85,3 +88,74 @@ def test_model_smooth_host_loop(cuda_device):
     assert env.collision_check_count > c0
     for p, q in zip(new[:-1], new[1:]):
         assert env._edge_fp(np.asarray(p), np.asarray(q))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# a5: the CALLER of the smoother forward -- reference smoother.py:194-246 -- against fixtures recorded while
+# the reference's own model_smooth / proposed_path_smootherv2 / MazeEnv / model_smoother.py ran (make_golden.more_goldens)
+def _a5_env():
+    from gnn_motion_planning_b200.environment import MazeEnv
+    mp = np.load(os.path.join(G, "maze_problems.npz"))
+    return MazeEnv(dim=2, map_file=os.path.join(G, "maze_problems.npz")), mp
+
+
+def test_steering_rounds_golden(cuda_device):
+    """proposed_path_smootherv2 (smoother.py:194-216) has no model in it: same inputs => the same path bit for bit and
+    the same collision_check_count, for every steering call the reference made (5 per problem)."""
+    from gnn_motion_planning_b200.smoother import proposed_path_smootherv2
+    gold = np.load(os.path.join(G, "model_smooth.npz"))
+    env, mp = _a5_env()
+    n = 0
+    for pid in gold["ids"]:
+        env.init_new_problem(int(np.flatnonzero(mp["ids"] == pid)[0]))
+        for j in range(int(gold["p%d_n_steer" % pid])):
+            old, new = gold["p%d_steer%d_old" % (pid, j)], gold["p%d_steer%d_new" % (pid, j)]
+            c0 = env.collision_check_count
+            out = proposed_path_smootherv2(list(old), list(new), env)
+            assert np.array_equal(np.array(out), gold["p%d_steer%d_out" % (pid, j)]), (pid, j)
+            assert env.collision_check_count - c0 == int(gold["p%d_steer%d_checks" % (pid, j)]), (pid, j)
+            n += 1
+    assert n == 30
+
+
+def test_model_smooth_golden(cuda_device):
+    """model_smooth (smoother.py:233-246): 5 x (smoother forward on the GPU -> steering rounds).  The forward is within 1e-4 of
+    the reference's, the steering thresholds (dist < RRT_EPS, collision booleans) amplify nothing on these problems: the
+    accepted path matches to 2e-4 and the collision-check count exactly."""
+    from gnn_motion_planning_b200.smoother import model_smooth
+    gold = np.load(os.path.join(G, "model_smooth.npz"))
+    env, mp = _a5_env()
+    m = make("smooth_2d_attv3.pt", 2, cuda_device)
+    for pid in gold["ids"]:
+        env.init_new_problem(int(np.flatnonzero(mp["ids"] == pid)[0]))
+        free = list(gold["p%d_ms_free" % pid])
+        coll = list(gold["p%d_ms_collided" % pid])
+        path = list(gold["p%d_ms_path" % pid])
+        c0 = env.collision_check_count
+        out = np.array(model_smooth(m, free, coll, path, env))
+        want = gold["p%d_ms_out" % pid]
+        assert out.shape == want.shape
+        assert np.abs(out - want).max() < 2e-4, (pid, np.abs(out - want).max())
+        assert env.collision_check_count - c0 == int(gold["p%d_ms_checks" % pid]), pid
+
+
+def test_explore_with_model_smoother_golden(cuda_device):
+    """explore(..., smoother='model') end to end (eval_gnn.py:168-276 -> smoother.py:233): success, explore / smooth check
+    counts and the smoothed path against the reference run with the same NumPy seed."""
+    from gnn_motion_planning_b200.eval_gnn import explore, path_cost
+    from gnn_motion_planning_b200.model import EncoderProcessDecoder
+    gold = np.load(os.path.join(G, "model_smooth.npz"))
+    env, mp = _a5_env()
+    model = EncoderProcessDecoder(workspace_size=2, config_size=2, embed_size=32, obs_size=2).to(cuda_device)
+    model.load_state_dict(torch.load(os.path.join(G, "weights", "weights_maze.pt"), map_location="cpu"))
+    ms = make("smooth_2d_attv3.pt", 2, cuda_device)
+    for pid in gold["ids"]:
+        np.random.seed(4321 + int(pid))
+        env.init_new_problem(int(np.flatnonzero(mp["ids"] == pid)[0]))
+        r = explore(env, model, ms, smooth=True, batch=100, t_max=100, k=10, smoother="model")
+        assert r["success"] == bool(gold["p%d_success" % pid])
+        assert r["c_explore"] == int(gold["p%d_c_explore" % pid])
+        assert np.allclose(np.array(r["path"]), gold["p%d_path" % pid])
+        assert r["c_smooth"] == int(gold["p%d_c_smooth" % pid]), pid
+        assert np.abs(np.array(r["smooth_path"]) - gold["p%d_smooth_path" % pid]).max() < 2e-4
+        assert path_cost(r["smooth_path"]) <= path_cost(r["path"]) + 1e-6

@@ -72,12 +72,16 @@ def test_knn_graph_properties():
     assert np.all(np.isin(np.arange(300) * 301, key))                  # self loops (loop=True)
 
 
-EXPLORER_CASES = [("maze2", "weights_maze.pt"), ("kuka7", "weights_kuka.pt"), ("kuka14", "kuka_14.pt")]
+# every (config, embed, obs) combination of reference str2name.py:12-66; the last four live in explorer_more.npz (round 2)
+EXPLORER_CASES = [("maze2", "weights_maze.pt"), ("kuka7", "weights_kuka.pt"), ("kuka14", "kuka_14.pt"),
+                  ("snake7", "weights_snake.pt"), ("ur5", "weights_ur5.pt"), ("kuka13", "weights_kuka_13.pt"),
+                  ("maze3", "weights_maze_3.pt")]
+EXPLORER_MORE = ("snake7", "ur5", "kuka13", "maze3")
 
 
 @pytest.mark.parametrize("tag,wfile", EXPLORER_CASES)
 def test_explorer_oracle_matches_reference(tag, wfile):
-    ex = np.load(os.path.join(G, "explorer.npz"))
+    ex = np.load(os.path.join(G, "explorer_more.npz" if tag in EXPLORER_MORE else "explorer.npz"))
     sd = torch.load(os.path.join(G, "weights", wfile), map_location="cpu")
     v, ei = torch.from_numpy(ex[tag + "_v"]), torch.from_numpy(ex[tag + "_edge_index"])
     obs, goal = torch.from_numpy(ex[tag + "_obstacles"]), torch.from_numpy(ex[tag + "_goal"])
@@ -106,14 +110,21 @@ def test_explorer_permutation_equivariance():
     assert torch.allclose(a, b[inv][:, inv], atol=1e-9)
 
 
-@pytest.mark.parametrize("tag,wfile", [("2d", "smooth_2d_attv3.pt"), ("7d", "smooth_7d_attv3.pt"), ("2d_short", "smooth_2d_attv3.pt")])
+SMOOTHER_CASES = [("2d", "smooth_2d_attv3.pt"), ("7d", "smooth_7d_attv3.pt"), ("2d_short", "smooth_2d_attv3.pt"),
+                  ("14d", "smooth_14d_attv3.pt"), ("13d", "smooth_13d_attv3.pt"), ("ur5", "smooth_ur5_attv3.pt"),
+                  ("snake", "smooth_snake_attv3.pt")]
+SMOOTHER_MORE = ("14d", "13d", "ur5", "snake")
+
+
+@pytest.mark.parametrize("tag,wfile", SMOOTHER_CASES)
 def test_smoother_oracle_matches_reference(tag, wfile):
-    sm = np.load(os.path.join(G, "smoother.npz"))
+    sm = np.load(os.path.join(G, "smoother_more.npz" if tag in SMOOTHER_MORE else "smoother.npz"))
     sd = torch.load(os.path.join(G, "weights", wfile), map_location="cpu")
+    scale = float(sm[tag + "_scale"]) if tag in SMOOTHER_MORE else 1.0          # ur5: 2*pi (str2name.py:40)
     for loop in (1, 3):
         got = smoother.smoother_forward(sd, torch.from_numpy(sm[tag + "_path"]), torch.from_numpy(sm[tag + "_free"]),
                                         torch.from_numpy(sm[tag + "_collided"]), torch.from_numpy(sm[tag + "_edge_index"]),
-                                        loop=loop).numpy()
+                                        loop=loop, scale=scale).numpy()
         want = sm["%s_out_loop%d" % (tag, loop)]
         assert np.abs(got - want).max() < 1e-5
         assert np.array_equal(got[0], sm[tag + "_path"][0]) and np.array_equal(got[-1], sm[tag + "_path"][-1])

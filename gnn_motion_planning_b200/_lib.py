@@ -46,6 +46,9 @@ SIGNATURES = {
                                       c_void_p, c_void_p, ctypes.c_double, c_void_p, c_void_p, c_void_p]),
     "gmp_arm_edge_fp_graph_cached": (c_int, [c_int, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
                                              c_void_p, c_void_p, ctypes.c_double, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "gmp_arm_edge_graph_workspace_bytes": (c_int64, [c_int64, c_int64]),
+    "gmp_arm_edge_fp_graph_fast": (c_int, [c_int, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
+                                           c_void_p, c_void_p, c_int, ctypes.c_double, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "gmp_smoother_init": (c_int, [c_void_p, c_int, c_int]),
     "gmp_smoother_set_tensor": (c_int, [c_void_p, c_char_p, c_void_p, c_int64]),
     "gmp_smoother_finalize": (c_int, [c_void_p]),

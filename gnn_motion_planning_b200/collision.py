@@ -164,10 +164,53 @@ def arm_edge_fp(model, a, b, boxes, box_ptr, problem=None, rrt_eps=0.5, want_che
     return (free, checks) if want_checks else free
 
 
+_arm_ws = {}          # device index -> scratch of the fast graph form (grown on demand, reused across calls)
+_max_boxes = {}       # (data_ptr, numel) of a box_ptr tensor -> its largest per-problem box count
+
+
+def _max_boxes_of(box_ptr):
+    key = (box_ptr.data_ptr(), box_ptr.numel())
+    if key not in _max_boxes:
+        if len(_max_boxes) > 64:
+            _max_boxes.clear()
+        _max_boxes[key] = int((box_ptr[1:] - box_ptr[:-1]).max()) if box_ptr.numel() > 1 else 0
+    return _max_boxes[key]
+
+
+def arm_last_undecided(device):
+    """Number of interpolated states the fp32 filter of the last fast-form call on `device` left to the exact fp64 kernel
+    (diagnostics; synchronises)."""
+    idx = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    ws, off = _arm_ws.get(idx), _arm_ws.get((idx, "counter_off"))
+    if ws is None or off is None:
+        return 0
+    return int(ws[off:off + 4].view(torch.int32)[0])
+
+
 @torch.no_grad()
 def arm_edge_fp_graph(model, v, edge_index, node_ptr_d, edge_ptr_d, boxes, box_ptr, n_edges_total, rrt_eps=0.5,
-                      problem_of_graph=None, want_checks=False, free_out=None, checks_out=None):
+                      problem_of_graph=None, want_checks=False, free_out=None, checks_out=None, mode="fast"):
+    """Every edge of a packed batch of graphs against its problem's boxes (kuka_env.py:389-411, one launch set).
+    mode "fast" (default): fp32 filter + exact fp64 decision of the undecided states, lanes pulling edges from per-CTA
+    queues; mode "exact": the fp64 thread-per-edge form.  Bit-identical results (tests/test_gpu_arm.py)."""
     lib = _lib.load()
+    if mode == "fast":
+        _lib.handle(_dev_index(v))
+        B = node_ptr_d.numel() - 1
+        free = free_out if free_out is not None else torch.empty(n_edges_total, dtype=torch.uint8, device=v.device)
+        checks = checks_out
+        if want_checks and checks is None:
+            checks = torch.empty(n_edges_total, dtype=torch.int32, device=v.device)
+        need = lib.gmp_arm_edge_graph_workspace_bytes(v.shape[0], n_edges_total)
+        ws = _arm_ws.get(_dev_index(v))
+        if ws is None or ws.numel() < need:
+            ws = _arm_ws[_dev_index(v)] = torch.empty(int(need * 1.1) + 1024, dtype=torch.uint8, device=v.device)
+        _arm_ws[(_dev_index(v), "counter_off")] = (v.shape[0] + 255) // 256 * 256
+        _lib.check(lib.gmp_arm_edge_fp_graph_fast(int(model), _lib.ptr(v), v.shape[0], _lib.ptr(edge_index), edge_index.stride(0),
+                                                  _lib.ptr(node_ptr_d), _lib.ptr(edge_ptr_d), _lib.ptr(problem_of_graph), B, n_edges_total,
+                                                  _lib.ptr(boxes), _lib.ptr(box_ptr), _max_boxes_of(box_ptr), float(rrt_eps), _lib.ptr(ws),
+                                                  ws.numel(), _lib.ptr(free), _lib.ptr(checks), _lib.stream_ptr(v.device)))
+        return (free, checks) if want_checks else free
     _lib.handle(_dev_index(v))
     B = node_ptr_d.numel() - 1
     free = free_out if free_out is not None else torch.empty(n_edges_total, dtype=torch.uint8, device=v.device)

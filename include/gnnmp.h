@@ -170,6 +170,19 @@ int gmp_arm_edge_fp_graph_cached(int model, const float* v, int64_t n_nodes_tota
                                  const int32_t* box_ptr, double rrt_eps, uint8_t* node_flags_ws, uint8_t* free_out,
                                  int32_t* n_checks_out, void* stream);
 
+/* The same result again (booleans and check counts bit-identical to gmp_arm_edge_fp_graph / oracle/arm.c), reached faster:
+ * every interpolated state goes through an fp32 evaluation of the model that decides it only when no sphere test is within
+ * 2.5e-4 m of touching (the fp32 forward kinematics are within ~3e-5 m of the fp64 ones); the undecided states (~1 %) are
+ * listed and decided by the exact fp64 test in a second kernel; lanes pull edges from a per-CTA queue instead of owning one.
+ * max_boxes_per_problem: the largest box count of any problem referenced (> 160 routes to the fp64 form).
+ * workspace: gmp_arm_edge_graph_workspace_bytes(n_nodes_total, n_edges_total) bytes of device scratch. */
+int64_t gmp_arm_edge_graph_workspace_bytes(int64_t n_nodes_total, int64_t n_edges_total);
+int gmp_arm_edge_fp_graph_fast(int model, const float* v, int64_t n_nodes_total, const int64_t* edge_index,
+                               int64_t edge_row_stride, const int32_t* node_ptr, const int32_t* edge_ptr,
+                               const int32_t* problem_of_graph, int64_t n_graphs, int64_t n_edges_total, const double* boxes,
+                               const int32_t* box_ptr, int max_boxes_per_problem, double rrt_eps, void* workspace,
+                               int64_t workspace_bytes, uint8_t* free_out, int32_t* n_checks_out, void* stream);
+
 /* ---- smoother: ModelSmoother (model_smoother.py:46-142) --------------------------------------- */
 int gmp_smoother_init(gmp_handle* h, int config_size /*c*/, int embed_size /*128*/);
 /* load_state_dict (eval_gnn.py:104) by reference tensor name, e.g. "node_code.1.running_mean"; dead tensors ignored. */

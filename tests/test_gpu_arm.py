@@ -148,3 +148,51 @@ def test_snake_and_ur5_env(cuda_device, probs):
     assert str(u) == "ur5" and u.config_dim == 6 and u.RRT_EPS == 0.1 and abs(np.max(u.bound) - 2 * np.pi) < 1e-9
     u.init_new_problem(5)
     assert u._state_fp(np.asarray(u.init_state, dtype=np.float64)) and u.in_goal_region(np.asarray(u.goal_state, dtype=np.float64))
+
+
+@pytest.mark.parametrize("tag,model,dof,eps", [("kuka7", 0, 7, 0.5), ("kuka14", 1, 14, 0.5), ("kuka13", 2, 13, 0.5), ("ur5", 3, 6, 0.1),
+                                               ("snake7", 4, 7, 0.1)])
+def test_fast_graph_form_is_bit_identical(cuda_device, probs, tag, model, dof, eps):
+    """The fp32-filter + exact-fixup graph kernel (default) against the fp64 thread-per-edge form and the C oracle: the same
+    booleans and the same collision_check_count increments on k-NN graphs of every arm model (boxes, ground plane,
+    self collision, arm-arm, > 32 boxes = the clustered path for the snake mazes)."""
+    from gnn_motion_planning_b200 import collision, graph
+    from oracle import arm as o_arm
+    dev = cuda_device
+    if tag == "snake7":
+        boxes, ptr = o_arm.snake_boxes(probs["snake7_maps"])
+    else:
+        boxes, ptr = probs[tag + "_boxes"], probs[tag + "_box_ptr"]
+    _, lo, hi = collision.arm_model_info(model)
+    rng = np.random.default_rng(11)
+    B, n, k = 6, 400, 12
+    v = rng.uniform(lo, hi, (B * n, dof)).astype(np.float32)
+    if tag == "snake7":          # keep the snake near its maze so that edges are short enough to be interesting
+        v[:, :2] = rng.uniform(-9, 9, (B * n, 2)).astype(np.float32)
+    v[[3, 401, 999]] *= 1.5      # nodes outside the joint limits
+    vd = torch.from_numpy(v).to(dev)
+    node_ptr = (np.arange(B + 1) * n).astype(np.int32)
+    ei, edge_ptr = graph.knn_graph_batch(vd, node_ptr, np.full(B, n), np.full(B, k))
+    et = int(edge_ptr[-1])
+    bd, pd = torch.from_numpy(boxes).to(dev), torch.from_numpy(ptr).to(dev)
+    pg_np = rng.integers(0, len(ptr) - 1, B).astype(np.int32)
+    pg = torch.from_numpy(pg_np).to(dev)
+    npd, epd = torch.from_numpy(node_ptr).to(dev), torch.from_numpy(edge_ptr).to(dev)
+    out = {}
+    for mode in ("fast", "exact"):
+        f, c = collision.arm_edge_fp_graph(model, vd, ei, npd, epd, bd, pd, et, rrt_eps=eps, problem_of_graph=pg, want_checks=True,
+                                           mode=mode)
+        out[mode] = (f.cpu().numpy().copy(), c.cpu().numpy().copy())
+    assert np.array_equal(out["fast"][0], out["exact"][0])
+    assert np.array_equal(out["fast"][1], out["exact"][1])
+    # and against the oracle on a sample of edges
+    ei_np = ei[:, :et].cpu().numpy()
+    gid = np.repeat(np.arange(B), np.diff(edge_ptr))
+    pick = rng.choice(et, 4000, replace=False)
+    a, b = v[ei_np[0, pick] + node_ptr[gid[pick]]], v[ei_np[1, pick] + node_ptr[gid[pick]]]
+    of, oc = o_arm.edge_fp(model, a, b, boxes, ptr, pg_np[gid[pick]], rrt_eps=eps)
+    assert np.array_equal(out["fast"][0][pick], of) and np.array_equal(out["fast"][1][pick], oc)
+    free_frac = out["fast"][0].mean()
+    undecided = collision.arm_last_undecided(dev)
+    print("%s: %d edges, free fraction %.3f, states checked %d, undecided by the fp32 filter %d" % (tag, et, free_frac, int(out["fast"][1].sum()), undecided))
+    assert 0.0 < free_frac < 1.0

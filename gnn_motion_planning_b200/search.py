@@ -1,0 +1,192 @@
+"""Batched planner loop: reference ``eval_gnn.explore`` (eval_gnn.py:168-276) for MANY maze problems at once, with the
+inner lazy tree search on the device.
+
+The reference runs one problem at a time: sample -> ``create_data`` -> ``model(...)`` -> a host loop that takes the arg-max of a
+masked dense policy and collision-checks ONE edge per Python iteration.  ``explore_batch`` keeps the semantics problem by
+problem -- same samples (each problem owns a NumPy ``RandomState`` whose stream is the one ``np.random.seed(seed)`` would give
+the reference), same graphs, same search order, same ``collision_check_count`` -- and runs every stage as one batched launch:
+
+    sampling     ``gmp_maze_state_fp`` over the draws of all active problems (the RNG stream stays on the host: the reference
+                 couples every draw to the outcome of the previous check, ``maze_env.py:85-100``)
+    graphs       ``gmp_knn_graph``         (``create_data``, eval_gnn.py:150-165)
+    logits       ``gmp_explorer_forward``  (sparse ``[E]``; the dense ``[N,N]`` matrix never exists)
+    search       ``gmp_maze_tree_search``  one CTA per problem, optional speculative edge checks (``spec_k``)
+
+Problems that exhaust their graph are resampled and continue in the next round (eval_gnn.py:235-247) with their tree, their
+explored-edge list and their counters kept on the device.
+"""
+import numpy as np
+import torch
+
+from . import _lib, collision, graph
+from .environment.env_config import LIMITS, RRT_EPS
+
+STATUS_SUCCESS, STATUS_EXHAUSTED, STATUS_CAPACITY = 1, 2, 3
+
+
+class TreeSearchState:
+    """Persistent per-problem search state on the device (one row per problem)."""
+
+    def __init__(self, n_problems, cap_nodes, cap_explored_edges, device):
+        z = lambda *shape: torch.zeros(*shape, dtype=torch.int32, device=device)  # noqa: E731
+        self.S, self.cap_nodes, self.cap_elist = n_problems, int(cap_nodes), int(cap_explored_edges)
+        self.explored, self.prev, self.path = z(n_problems, cap_nodes), z(n_problems, cap_nodes), z(n_problems, cap_nodes)
+        self.elist = z(n_problems, cap_explored_edges)
+        self.n_explored, self.n_elist, self.n_checks, self.n_spec = z(n_problems), z(n_problems), z(n_problems), z(n_problems)
+        self.status, self.path_len = z(n_problems), z(n_problems)
+        self._ws = None
+
+    def workspace(self, nbytes, device):
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = torch.empty(int(nbytes * 1.1) + 1024, dtype=torch.uint8, device=device)
+        return self._ws
+
+
+@torch.no_grad()
+def maze_tree_search(state, v, node_ptr_d, n_free_d, edge_index, edge_ptr_d, logits, goal64, maps, problem_of_graph, slot_of_graph,
+                     n_nodes_total, n_edges_total, spec_k=1, first_round=True):
+    """One search round for a packed batch of graphs (see ``gmp_maze_tree_search`` in include/gnnmp.h).  All arguments are CUDA
+    tensors except the three integers; results land in ``state``."""
+    lib = _lib.load()
+    for name, t in (("v", v), ("edge_index", edge_index), ("logits", logits), ("goal64", goal64), ("maps", maps)):
+        _lib.require_cuda(t, name)
+    if maps.dtype != torch.uint8 or goal64.dtype != torch.float64 or logits.dtype != torch.float32:
+        raise TypeError("maps must be uint8, goal float64, logits float32")
+    B = node_ptr_d.numel() - 1
+    ws = state.workspace(lib.gmp_tree_search_workspace_bytes(B, n_nodes_total, n_edges_total), v.device)
+    _lib.check(lib.gmp_maze_tree_search(
+        _lib.ptr(v), _lib.ptr(node_ptr_d), _lib.ptr(n_free_d), _lib.ptr(edge_index), edge_index.stride(0), _lib.ptr(edge_ptr_d),
+        _lib.ptr(logits), _lib.ptr(goal64), _lib.ptr(maps), _lib.ptr(problem_of_graph), _lib.ptr(slot_of_graph), B, n_nodes_total,
+        n_edges_total, int(spec_k), int(bool(first_round)), _lib.ptr(state.explored), _lib.ptr(state.n_explored), _lib.ptr(state.prev),
+        _lib.ptr(state.elist), _lib.ptr(state.n_elist), _lib.ptr(state.n_checks), _lib.ptr(state.n_spec), _lib.ptr(state.status),
+        _lib.ptr(state.path), _lib.ptr(state.path_len), state.cap_nodes, state.cap_elist, _lib.ptr(ws), ws.numel(),
+        _lib.stream_ptr(v.device)))
+
+
+def _sample_batch(rngs, need, maps_d, problem_ids, device):
+    """``env.sample_n_points(need[p], need_negative=True)`` (maze_env.py:85-100) for several problems at once: the draws of all
+    problems go through ONE state-check launch per pass; every RandomState ends exactly where the reference's would."""
+    P = len(rngs)
+    free = [[] for _ in range(P)]
+    coll = [[] for _ in range(P)]
+    counted = np.zeros(P, np.int64)
+    todo = [p for p in range(P) if need[p] > 0]
+    while todo:
+        states, draws = {}, {}
+        for p in todo:
+            chunk = max(64, int((need[p] - len(free[p])) * 2.5))
+            states[p] = rngs[p].get_state()
+            draws[p] = rngs[p].uniform(-LIMITS[:2], LIMITS[:2], (chunk, 2))
+        allp = np.concatenate([draws[p] for p in todo])
+        prob = np.concatenate([np.full(len(draws[p]), problem_ids[p], np.int32) for p in todo])
+        ok = collision.maze_state_fp(torch.from_numpy(allp).to(device), maps_d, torch.from_numpy(prob).to(device)).cpu().numpy().astype(bool)
+        off, nxt = 0, []
+        for p in todo:
+            d, f = draws[p], ok[off:off + len(draws[p])]
+            off += len(d)
+            missing = need[p] - len(free[p])
+            idx = np.flatnonzero(f)
+            used = len(d) if len(idx) < missing else int(idx[missing - 1]) + 1
+            if used < len(d):               # rewind: consume exactly the draws the reference would have made
+                rngs[p].set_state(states[p])
+                d = rngs[p].uniform(-LIMITS[:2], LIMITS[:2], (used, 2))
+                f = f[:used]
+            counted[p] += used              # every draw lies inside the limits: one counted lookup each (maze_env.py:272-276)
+            for s_, f_ in zip(d, f):
+                (free[p] if f_ else coll[p]).append(s_)
+            if len(free[p]) < need[p]:
+                nxt.append(p)
+        todo = nxt
+    return free, coll, counted
+
+
+@torch.no_grad()
+def explore_batch(model, maps, init_states, goal_states, problem_ids, seeds, batch=100, t_max=100, k=10, loop=5, spec_k=1,
+                  device=None, max_checks=20000):
+    """``explore(env, model, None, smooth=True, batch, t_max, k, smoother='none')`` for every problem of ``problem_ids``
+    (rows of ``maps`` / ``init_states`` / ``goal_states``), seeded like ``np.random.seed(seeds[i])`` before the reference call.
+
+    Returns one dict per problem: success, path (float32 waypoints), path_nodes, explored (node ids in tree order), c_explore
+    (= env.collision_check_count delta: sampling + edge + goal-region checks), spec_checks (speculative edge checks that were
+    never committed; 0 when spec_k == 1), n_nodes, rounds."""
+    dev = torch.device(device if device is not None else "cuda")
+    P = len(problem_ids)
+    problem_ids = [int(p) for p in problem_ids]
+    maps_d = torch.as_tensor(np.ascontiguousarray(np.asarray(maps) != 0).astype(np.uint8)).to(dev)
+    rngs = [np.random.RandomState(int(s)) for s in seeds]
+    goal64 = torch.from_numpy(np.ascontiguousarray(np.asarray(goal_states, np.float64)[problem_ids])).to(dev)
+    n_batch = batch
+    cap_nodes = 2 * (t_max + 2 * n_batch + 2) + 8
+    st = TreeSearchState(P, cap_nodes, 2 + 4 * max_checks, dev)
+
+    new_free, new_coll, counted = _sample_batch(rngs, [n_batch] * P, maps_d, problem_ids, dev)
+    free = [[np.asarray(init_states[problem_ids[p]]), np.asarray(goal_states[problem_ids[p]])] + new_free[p] for p in range(P)]
+    coll = [new_coll[p][:len(new_free[p])] for p in range(P)]                      # collided = collided[:len(free)] BEFORE init/goal join (:180-181)
+    c_sample = counted.copy()
+    active = list(range(P))
+    rounds = np.zeros(P, np.int64)
+    last_v = [None] * P
+    first = True
+    while active:
+        # ---- create_data for every active problem (eval_gnn.py:150-165), packed
+        vs, n_free, k1 = [], [], []
+        for p in active:
+            f = np.asarray(free[p], np.float64).reshape(len(free[p]), 2)
+            c = np.asarray(coll[p], np.float64).reshape(len(coll[p]), 2)
+            vs.append(np.concatenate([f, c]).astype(np.float32))                  # torch.FloatTensor(np.array(...))
+            n_free.append(len(f))
+            k1.append(graph.k1_of(k, len(f)))
+            last_v[p] = vs[-1]
+        node_ptr = np.concatenate([[0], np.cumsum([len(x) for x in vs])]).astype(np.int32)
+        v_d = torch.from_numpy(np.concatenate(vs)).to(dev)
+        ei, edge_ptr = graph.knn_graph_batch(v_d, node_ptr, np.asarray(n_free, np.int32), np.asarray(k1, np.int32))
+        et = int(edge_ptr[-1])
+        # ---- model(**data, **obs_data, loop=loop): sparse logits (eval_gnn.py:194)
+        obss = [(np.argwhere(np.asarray(maps[problem_ids[p]]) == 1) / 15.0 - 0.5).astype(np.float32) for p in active]   # maze_env.py:73-79
+        obs_ptr = np.concatenate([[0], np.cumsum([len(o) for o in obss])]).astype(np.int32)
+        obs_d = torch.from_numpy(np.concatenate(obss).reshape(-1, 2)).to(dev)
+        goal_d = torch.from_numpy(np.stack([np.asarray(goal_states[problem_ids[p]], np.float32) for p in active])).to(dev)
+        logits = model.forward_batch(v_d, ei, goal_d, obs_d, node_ptr, edge_ptr, obs_ptr, loop=loop)
+        # ---- the search itself
+        slots = torch.tensor(active, dtype=torch.int32, device=dev)
+        probs = torch.tensor([problem_ids[p] for p in active], dtype=torch.int32, device=dev)
+        maze_tree_search(st, v_d, torch.from_numpy(node_ptr).to(dev), torch.tensor(n_free, dtype=torch.int32, device=dev), ei,
+                         torch.from_numpy(edge_ptr).to(dev), logits, goal64, maps_d, probs, slots, int(node_ptr[-1]), et,
+                         spec_k=spec_k, first_round=first)
+        first = False
+        status = st.status.cpu().numpy()
+        nxt = []
+        for p in active:
+            rounds[p] += 1
+            if status[p] == STATUS_CAPACITY:
+                raise _lib.GnnmpError("tree search capacity exceeded for problem %d (raise max_checks)" % problem_ids[p])
+            if status[p] == STATUS_EXHAUSTED and (n_batch + len(free[p]) - 2) <= t_max:      # eval_gnn.py:239-240
+                nxt.append(p)
+        if nxt:                                                                               # resample (:242-247)
+            nf, nc, cnt = _sample_batch([rngs[p] for p in nxt], [n_batch] * len(nxt), maps_d, [problem_ids[p] for p in nxt], dev)
+            for i, p in enumerate(nxt):
+                free[p] = free[p] + nf[i]
+                coll[p] = (coll[p] + nc[i])[:len(free[p])]
+                c_sample[p] += cnt[i]
+        active = nxt
+    # ---- results
+    status = st.status.cpu().numpy()
+    n_expl, n_chk, n_spec, plen = (t.cpu().numpy() for t in (st.n_explored, st.n_checks, st.n_spec, st.path_len))
+    explored, path = st.explored.cpu().numpy(), st.path.cpu().numpy()
+    out = []
+    for p in range(P):
+        ok = status[p] == STATUS_SUCCESS
+        nodes = path[p, :plen[p]].tolist() if ok else []
+        out.append(dict(success=bool(ok), path_nodes=nodes, path=[last_v[p][i] for i in nodes], explored=explored[p, :n_expl[p]].tolist(),
+                        c_explore=int(c_sample[p] + n_chk[p]), c_search=int(n_chk[p]), spec_checks=int(n_spec[p]), n_nodes=len(last_v[p]),
+                        rounds=int(rounds[p])))
+    return out
+
+
+def path_cost(path):
+    """eval_gnn.py:53-58."""
+    path = np.array(path)
+    return float(sum(np.linalg.norm(path[i + 1] - path[i]) for i in range(len(path) - 1)))
+
+
+__all__ = ["TreeSearchState", "maze_tree_search", "explore_batch", "path_cost", "RRT_EPS"]

@@ -136,6 +136,32 @@ int gmp_maze_edge_fp_graph(const float* v, const int64_t* edge_index, int64_t ed
                            int64_t n_edges_total, const uint8_t* maps, uint8_t* free_out, int32_t* n_checks_out,
                            void* stream);
 
+/* ---- batched lazy tree search: the inner loop of explore() (eval_gnn.py:198-233), maze environments ------------ */
+/* One CTA per problem replays the reference's search on the SPARSE logits of gmp_explorer_forward: masks of eval_gnn.py:198-202
+ * (diagonal, explored columns, collided rows / columns = nodes >= n_free[g], the explored-edge list with the reference's
+ * reshape(2,-1) quirk), then repeatedly: arg-max over the rows of the explored nodes (ties: earlier position in `explored`,
+ * then lower column), env._edge_fp on that edge, grow the tree (and test in_goal_region) or zero the edge both ways.
+ * Stops on success (status 1), when no candidate is left (status 2: the caller resamples, rebuilds the graph and calls again
+ * with first_round = 0), or when a capacity is exceeded (status 3).
+ *   v, node_ptr (DEVICE [B+1]), n_free (DEVICE [B]), edge_index / edge_ptr (DEVICE [B+1]), edge_logits: this round's packed batch
+ *   goal [S,2] f64: env.goal_state per slot;  maps [P,15,15] u8;  problem_of_graph [B] (NULL = g);  slot_of_graph [B] (NULL = g):
+ *   which row of the persistent search state graph g continues
+ *   spec_k in [1,32]: edges checked per iteration (1 = the reference's one edge; more = speculative checks of the next-best
+ *   candidates, remembered and committed later in the reference's order -- results are identical for every spec_k)
+ *   persistent state, S rows: explored [S,cap_nodes], n_explored [S], prev [S,cap_nodes], explored_edges [S,cap_explored_edges]
+ *   (the flat list of eval_gnn.py:184,214), n_explored_edges [S], n_checks [S] (collision_check_count increments of the search:
+ *   edge checks + the in_goal_region state checks), n_spec_checks [S] (speculative checks never committed), status [S],
+ *   path [S,cap_nodes] + path_len [S] (node ids from 0 to the goal-region node, eval_gnn.py:223-229). */
+int64_t gmp_tree_search_workspace_bytes(int64_t n_graphs, int64_t n_nodes_total, int64_t n_edges_total);
+int gmp_maze_tree_search(const float* v, const int32_t* node_ptr, const int32_t* n_free, const int64_t* edge_index,
+                         int64_t edge_row_stride, const int32_t* edge_ptr, const float* edge_logits, const double* goal,
+                         const uint8_t* maps, const int32_t* problem_of_graph, const int32_t* slot_of_graph,
+                         int64_t n_graphs, int64_t n_nodes_total, int64_t n_edges_total, int spec_k, int first_round,
+                         int32_t* explored, int32_t* n_explored, int32_t* prev, int32_t* explored_edges,
+                         int32_t* n_explored_edges, int32_t* n_checks, int32_t* n_spec_checks, int32_t* status,
+                         int32_t* path, int32_t* path_len, int32_t cap_nodes, int32_t cap_explored_edges,
+                         void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- arm collision: KukaEnv / Kuka2Env (environment/kuka_env.py, kuka_2arm_env.py) ------------- */
 /* The reference queries PyBullet contact points; this library substitutes its own geometric model (DESIGN.md:
  * FK down the URDF joint chain, link hulls filled with inscribed spheres, boxes as AABBs) -- parity with PyBullet

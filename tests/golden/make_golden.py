@@ -450,6 +450,27 @@ def more_goldens():
     a5["ids"] = np.array(ids)
     np.savez_compressed(os.path.join(HERE, "model_smooth.npz"), **a5)
 
+    # ---------------------------------------------------------------- explore() with RESAMPLING rounds (eval_gnn.py:235-247)
+    # small batches so that the first graphs are exhausted: the tree, the explored-edge list (with the reshape(2,-1) quirk of
+    # eval_gnn.py:202) and the counters carry over to the next graph.  smoother='none'.
+    ns["model_smooth"] = ns_s["model_smooth"]
+    mr = {}
+    cases = [(pid, b, t, kk) for pid in (2000, 2001, 2002, 2003, 2004, 2005) for (b, t, kk) in ((25, 200, 6), (40, 300, 8))]
+    for pid, b, t, kk in cases:
+        np.random.seed(777 + pid)
+        env.init_new_problem(pid)
+        r = ns["explore"](env, m, None, smooth=True, batch=b, t_max=t, k=kk, smoother="none")
+        tag = "p%d_b%d" % (pid, b)
+        mr[tag + "_success"] = np.array(r["success"])
+        mr[tag + "_c_explore"] = np.array(r["c_explore"])
+        mr[tag + "_explored"] = np.array(r["explored"])
+        mr[tag + "_path"] = np.array(r["path"]) if r["success"] else np.zeros((0, 2), np.float32)
+        mr[tag + "_n_nodes"] = np.array(len(r["data"].v))
+        mr[tag + "_n_explored_edges"] = np.array(len(r["explored_edges"]))
+        print("explore multi-round", tag, r["success"], r["c_explore"], len(r["explored"]), len(r["data"].v))
+    mr["cases"] = np.array(cases)
+    np.savez_compressed(os.path.join(HERE, "explore_rounds.npz"), **mr)
+
 
 if __name__ == "__main__":
     if "--more-only" not in sys.argv:

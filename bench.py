@@ -91,11 +91,7 @@ def run_mixed(args, wl, rank, local_rank, world):
     from gnn_motion_planning_b200.batch import HotPath
     from gnn_motion_planning_b200.model import EncoderProcessDecoder
     _lib.load()
-    torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
     ap = _arm_problems()
     maps_np = np.load(os.path.join(G, "maze_maps_256.npz"))["maps"]
     N, k = wl["n"], wl["k"]
@@ -205,9 +201,7 @@ def run_mixed(args, wl, rank, local_rank, world):
     e2e_finish()
     ms_e2e = timed_region(e2e_step, args.steps, finish=e2e_finish)
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return None
     K = args.steps
     Btot = wl["batch"]
     line = {
@@ -225,9 +219,7 @@ def run_mixed(args, wl, rank, local_rank, world):
         "gpu_launches": K * len(subs) * 27, "clocks": clocks,
         "note": "mixed sweep: roofline / cpu_baseline are reported by the single-environment workloads (C2, C3, C4)",
     }
-    _emit(line)
-    if world > 1:
-        dist.destroy_process_group()
+    return line
 
 
 def ref_oplist_flops(n, e_cnt, o, c, e, s, loop=5):
@@ -378,6 +370,8 @@ def main():
     ap.add_argument("--ref-graphs-per-step", type=int, default=4)
     ap.add_argument("--cpu-sample", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sub-records", action="store_true", help="only the headline workload (no C3/C4/C5/planner sub-records)")
+    ap.add_argument("--sub-steps", type=int, default=5)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     wl = WORKLOADS[args.workload]
@@ -385,30 +379,162 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
-    if args.workload == "C5":
-        if args.impl == "reference":
+    if args.impl == "reference":
+        if args.workload == "C5":
             if rank == 0:
                 _emit({"impl": "reference", "unavailable": "mixed sweep: run --workload C2/C3/C4 for the per-environment CPU port baseline"})
             return
-        run_mixed(args, wl, rank, local_rank, world)
-        return
-    if args.impl == "reference":
         run_reference(args, wl, rank, world)
         return
 
     import torch
     import torch.distributed as dist
-    from gnn_motion_planning_b200 import _lib, collision, graph
-    from gnn_motion_planning_b200.model import EncoderProcessDecoder
-
+    from gnn_motion_planning_b200 import _lib
     _lib.load()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    _pin_to_gpu_numa_node(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+
+    def run(name, steps, warmup, cpu_baseline):
+        a = argparse.Namespace(**vars(args))
+        a.workload, a.steps, a.warmup, a.no_cpu_baseline = name, steps, warmup, not cpu_baseline
+        line = run_mixed(a, WORKLOADS[name], rank, local_rank, world) if name == "C5" else run_single(a, WORKLOADS[name], rank, local_rank, world)
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        return line
+
+    line = run(args.workload, args.steps, args.warmup, world == 1 and not args.no_cpu_baseline)
+    if args.workload == "C2" and not args.no_sub_records:
+        # BASELINE.json configs[2..4] and the planner loop (configs[0] batched) as sub-records of the same JSON line.  C4 / C5 are
+        # the configs BASELINE defines as multi-GPU: at N ranks they run 128 / 256 problems per rank (1 024 / 2 048 at N = 8).
+        subs = {}
+        names = ["C3", "C4", "C5"] if world == 1 else ["C4", "C5"]
+        for name in names:
+            sub = run(name, args.sub_steps, 3, world == 1 and not args.no_cpu_baseline and name != "C5")
+            if rank == 0:
+                subs[name] = {k_: v_ for k_, v_ in sub.items() if k_ not in ("gpu_launches_note",)}
+        pl = run_planner(args, rank, local_rank, world)
+        if rank == 0:
+            subs["C1_planner"] = pl
+            line["sub_records"] = subs
+            line["gpu_launches"] += sum(int(v_.get("gpu_launches", 0)) for v_ in subs.values())
+    if rank == 0:
+        _emit(line)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _pin_to_gpu_numa_node(local_rank):
+    """Bind this rank's host threads (and therefore its pinned staging buffers, first-touch) to the CPUs next to its GPU:
+    round 1's 8-rank run had every rank on NUMA node 0 and lost a third of its end-to-end throughput to the read-back."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = [64 * w + b for w in range(n_words) for b in range(64) if (int(mask[w]) >> b) & 1]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
+
+
+def run_planner(args, rank, local_rank, world):
+    """BASELINE.json configs[0] batched: explore(batch=100, t_max=100, k=10, smoother='none') (main.ipynb cell 8) for 256 maze
+    problems per rank through gnn_motion_planning_b200.search.explore_batch -- sampling, graph build, forward and the lazy tree
+    search on the device (gmp_maze_tree_search), host code only between rounds.  Problems: the 256 real maps of maze_maps_256.npz
+    with init / goal drawn like MazeEnv.set_random_init_goal (seeded).  Reported beside the repo's own host mirror of the
+    reference loop (one problem at a time, one edge per Python iteration, same kernels) on a sample of the same problems."""
+    import torch
+    import torch.distributed as dist
+    from gnn_motion_planning_b200 import search
+    from gnn_motion_planning_b200.model import EncoderProcessDecoder
+    dev = torch.device("cuda", local_rank)
+    maps = np.load(os.path.join(G, "maze_maps_256.npz"))["maps"]
+    P = len(maps)
+    rng = np.random.default_rng(4242)
+    init, goal = np.zeros((P, 2)), np.zeros((P, 2))
+    for p in range(P):            # free cell centres, jittered: init != goal
+        free = np.argwhere(maps[p] == 0)
+        i, j = rng.choice(len(free), 2, replace=False)
+        init[p] = (free[i] + rng.uniform(0.3, 0.7, 2)) * 2.0 / 15 - 1.0
+        goal[p] = (free[j] + rng.uniform(0.3, 0.7, 2)) * 2.0 / 15 - 1.0
+    model = EncoderProcessDecoder(workspace_size=2, config_size=2, embed_size=32, obs_size=2).to(dev)
+    model.load_state_dict(torch.load(os.path.join(G, "weights", "weights_maze.pt"), map_location="cpu"))
+    ids = list(range(P))
+    seeds = [1234 + rank * P + p for p in ids]
+    out = {}
+    for spec_k in (1, 8):
+        search.explore_batch(model, maps, init, goal, ids[:32], seeds[:32], batch=100, t_max=100, k=10, spec_k=spec_k, device=dev)   # warm-up
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        res = search.explore_batch(model, maps, init, goal, ids, seeds, batch=100, t_max=100, k=10, spec_k=spec_k, device=dev)
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        out[spec_k] = (float(dt), res)
+    if rank != 0:
+        return None
+    dt, res = out[1]
+    # the reference's loop structure on the same kernels: one problem at a time, host arg-max, one edge check per iteration
+    from gnn_motion_planning_b200.eval_gnn import explore
+    n_host = 8
+    env = _SyntheticMazeEnv(maps, init, goal, dev)
+    t0 = time.perf_counter()
+    same = 0
+    for p in range(n_host):
+        np.random.seed(seeds[p])
+        env.init_new_problem(p)
+        h = explore(env, model, None, smooth=True, batch=100, t_max=100, k=10, smoother="none")
+        same += int(h["explored"] == res[p]["explored"] and h["c_explore"] == res[p]["c_explore"])
+    dt_host = time.perf_counter() - t0
+    return {
+        "metric": "planner_problems_per_sec", "value": P * world / dt, "unit": "problems/s", "n_gpus": world, "wall_s": dt,
+        "config": {"workload": "C1 batched: explore(batch=100, t_max=100, k=10, smoother='none') x %d maze problems/GPU (maze_maps_256.npz maps, "
+                               "seeded init/goal), sampling + create_data + forward + lazy tree search all batched" % P},
+        "success": sum(r["success"] for r in res), "problems": P,
+        "mean_collision_checks": float(np.mean([r["c_explore"] for r in res])), "mean_explored": float(np.mean([len(r["explored"]) for r in res])),
+        "spec_k8": {"value": P * world / out[8][0], "unit": "problems/s", "uncommitted_speculative_checks_per_problem": float(np.mean([r["spec_checks"] for r in out[8][1]])),
+                    "identical_results": all(a["explored"] == b["explored"] and a["c_explore"] == b["c_explore"] for a, b in zip(res, out[8][1]))},
+        "host_loop": {"value": n_host / dt_host, "unit": "problems/s", "sample": "first %d problems through eval_gnn.explore (reference loop, one edge per "
+                      "iteration, same CUDA kernels)" % n_host, "identical_results": same == n_host},
+        "published_reference": {"value": 11.66, "unit": "problems/s", "source": "main.ipynb raw line 140 (author's machine, unknown hardware; different random mazes)"},
+        "timing": "host wall clock around explore_batch (the loop has host code between rounds), max over ranks",
+        "gpu_launches": 12,
+    }
+
+
+class _SyntheticMazeEnv:
+    """Minimal MazeEnv over in-memory arrays for the host-loop comparison of run_planner (same kernels as the package's MazeEnv)."""
+
+    def __new__(cls, maps, init, goal, dev):
+        import tempfile
+        from gnn_motion_planning_b200.environment import MazeEnv
+        with tempfile.NamedTemporaryFile(suffix=".npz", delete=False) as f:
+            np.savez(f, maps=maps.astype(np.float64), init_states=init, goal_states=goal)
+            path = f.name
+        env = MazeEnv(dim=2, map_file=path, device=dev)
+        os.unlink(path)
+        return env
+
+
+def run_single(args, wl, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    from gnn_motion_planning_b200 import _lib, collision, graph
+    from gnn_motion_planning_b200.model import EncoderProcessDecoder
+    dev = torch.device("cuda", local_rank)
 
     B, N, c = wl["batch"], wl["n"], wl["c"]
     # ---- synthetic inputs of this rank's shard (problems rank*B .. rank*B+B-1), host side
@@ -479,7 +605,7 @@ def main():
         bufs = hp.compute(v_d, goal_d, obs_d, obs_ptr, prob_d, events=evs)
         if world > 1:   # the only collective: per-problem result rows
             dist.all_gather_into_tensor(gather_buf.view(world * B, 4), bufs["rows"])
-        state.update(et=bufs["et"], edge_ptr=bufs["edge_ptr"], rows=bufs["rows"], checks=bufs["checks"])
+        state.update(et=bufs["et"], edge_ptr=bufs["edge_ptr"], rows=bufs["rows"], checks=bufs["checks"], bufs=bufs)
         if sm is not None:
             se = (ev(), ev())
             se[0].record()
@@ -554,10 +680,29 @@ def main():
     e2e_finish()
     ms_e2e = timed_region(e2e_step, args.steps, finish=e2e_finish)
 
+    # ---- the drop-in output: dense [N,N] per graph (model.py:148-150) instead of the sparse [E] logits the batched path returns
+    dense_info = None
+    if args.workload == "C2":
+        n_dense = B * N * N
+        dense_buf = torch.empty(n_dense, dtype=torch.float32, device=dev)
+        ei_d, ep_h = state["bufs"]["ei"], state["bufs"]["edge_ptr"]
+        t_ = {}
+        for dense in (False, True):
+            for it in range(4):
+                a_, b_ = ev(), ev()
+                a_.record()
+                model.forward_batch(v_d, ei_d, goal_d, obs_d, node_ptr, ep_h, obs_ptr, loop=5, dense=dense, dense_out=dense_buf if dense else None)
+                b_.record()
+                b_.synchronize()
+                t_[dense] = a_.elapsed_time(b_)
+        dense_info = {"forward_ms_sparse": t_[False], "forward_ms_dense": t_[True], "dense_bytes_per_step": n_dense * 4,
+                      "note": "timed separately: the batched path (value, e2e) returns sparse [E] logits; the reference-shaped dense [N,N] "
+                              "matrices add a memset + scatter of %.2f GB per step on the device and would be %.1fx the current read-back"
+                              % (n_dense * 4 / 1e9, n_dense * 4 / max(io["d2h"], 1))}
+        del dense_buf
+
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return None
 
     K = args.steps
     graphs_per_s = B * world / (ms_step / 1000.0)
@@ -634,14 +779,15 @@ def main():
                              "{maze,arm}_edge_graph (arms: node_flags + edge_graph_cached) + result_rows + smoother 5 x (graph,node,msg,path); memsets/copies not counted",
         "clocks": clocks,
     }
+    if dense_info:
+        line["dense_output"] = dense_info
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        gps, dt, _ = cpu_graphs_per_sec(wl, list(range(args.cpu_sample)), threads)
+        n_s = args.cpu_sample if args.workload == "C2" else (4 if args.workload == "C3" else 2)
+        gps, dt, _ = cpu_graphs_per_sec(wl, list(range(n_s)), threads)
         line["cpu_baseline"] = {"value": gps, "unit": "graphs/s", "cores": threads, "kind": "port",
-                                "sample": "first %d graphs of the workload (oracle: knn graph + explorer forward + edge checks), %.1f s" % (args.cpu_sample, dt)}
-    _emit(line)
-    if world > 1:
-        dist.destroy_process_group()
+                                "sample": "first %d graphs of the workload (oracle: knn graph + explorer forward + edge checks), %.1f s" % (n_s, dt)}
+    return line
 
 
 if __name__ == "__main__":

@@ -172,7 +172,7 @@ struct SearchArgs {
   int32_t* in_ptr; int32_t* cursor; float* bestv; int32_t* bests; int32_t* csr_src; float* csr_val; int32_t* chk;
   // persistent search state, one row per slot
   int32_t* explored; int32_t* n_explored; int32_t* prev; int32_t* elist; int32_t* n_elist; int32_t* n_checks; int32_t* n_spec;
-  int32_t* status; int32_t* path; int32_t* path_len;
+  int32_t* status; int32_t* path; int32_t* path_len; float* path_cost;
   int cap_nodes, cap_elist;
 };
 
@@ -243,6 +243,7 @@ __global__ void __launch_bounds__(kSearchThreads) maze_tree_search_kernel(Search
     explored[0] = 0; A.n_explored[slot_id] = 1; prev[0] = 0;
     elist[0] = 0; elist[1] = 0; A.n_elist[slot_id] = 2;
     A.n_checks[slot_id] = 0; A.n_spec[slot_id] = 0; A.path_len[slot_id] = 0;
+    if (A.path_cost) A.path_cost[slot_id] = 0.f;
   }
   __syncthreads();
   int n_expl = A.n_explored[slot_id];
@@ -391,6 +392,15 @@ __global__ void __launch_bounds__(kSearchThreads) maze_tree_search_kernel(Search
       int i = len - 1;
       for (int node = explored[n_expl - 1];; node = prev[node]) { out[i--] = node; if (node == 0) break; }
       A.path_len[slot_id] = len;
+      if (A.path_cost) {                           // path_cost(path), eval_gnn.py:53-58: float32 norms accumulated in float32
+        float cost = 0.f;
+        for (int j = 0; j + 1 < len; ++j) {
+          const float2 p0 = vg[out[j]], p1 = vg[out[j + 1]];
+          const float dx = p1.x - p0.x, dy = p1.y - p0.y;
+          cost = cost + sqrtf(dx * dx + dy * dy);
+        }
+        A.path_cost[slot_id] = cost;
+      }
     }
   }
   // speculative checks that were never committed
@@ -402,6 +412,21 @@ __global__ void __launch_bounds__(kSearchThreads) maze_tree_search_kernel(Search
   for (int o = 16; o > 0; o >>= 1) wasted += __shfl_xor_sync(0xffffffffu, wasted, o);
   if (lane == 0 && wasted) atomicAdd(A.n_spec + slot_id, wasted);
   (void)n_spec;
+}
+
+// per-problem rows of the final reduction (eval_gnn.py:120-134): (problem id, success, path cost, collision checks of the search,
+// speculative checks never committed, explored nodes) -- the payload of the multi-GPU all-gather
+__global__ void search_rows_kernel(const int32_t* __restrict__ status, const float* __restrict__ path_cost, const int32_t* __restrict__ n_checks,
+                                   const int32_t* __restrict__ n_spec, const int32_t* __restrict__ n_explored, int first_problem, int n,
+                                   float* __restrict__ rows) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  rows[6 * i + 0] = (float)(first_problem + i);
+  rows[6 * i + 1] = status[i] == 1 ? 1.f : 0.f;
+  rows[6 * i + 2] = path_cost ? path_cost[i] : 0.f;
+  rows[6 * i + 3] = (float)n_checks[i];
+  rows[6 * i + 4] = (float)n_spec[i];
+  rows[6 * i + 5] = (float)n_explored[i];
 }
 
 inline int grid_for(int64_t n, int block) {
@@ -485,8 +510,8 @@ extern "C" int gmp_maze_tree_search(const float* v, const int32_t* node_ptr, con
                                     int64_t n_graphs, int64_t n_nodes_total, int64_t n_edges_total, int spec_k, int first_round,
                                     int32_t* explored, int32_t* n_explored, int32_t* prev, int32_t* explored_edges,
                                     int32_t* n_explored_edges, int32_t* n_checks, int32_t* n_spec_checks, int32_t* status,
-                                    int32_t* path, int32_t* path_len, int32_t cap_nodes, int32_t cap_explored_edges,
-                                    void* workspace, int64_t workspace_bytes, void* stream) {
+                                    int32_t* path, int32_t* path_len, float* path_cost, int32_t cap_nodes,
+                                    int32_t cap_explored_edges, void* workspace, int64_t workspace_bytes, void* stream) {
   GMP_REQUIRE(n_graphs >= 0 && n_nodes_total >= 0 && n_edges_total >= 0, "negative size");
   if (n_graphs == 0) return GMP_OK;
   GMP_REQUIRE(v && node_ptr && n_free && edge_ptr && goal && maps && (edge_index || n_edges_total == 0) && (edge_logits || n_edges_total == 0),
@@ -506,9 +531,20 @@ extern "C" int gmp_maze_tree_search(const float* v, const int32_t* node_ptr, con
   A.cursor = cv.take<int32_t>(n_nodes_total); A.bestv = cv.take<float>(n_nodes_total); A.bests = cv.take<int32_t>(n_nodes_total);
   A.csr_src = cv.take<int32_t>(n_edges_total); A.csr_val = cv.take<float>(n_edges_total); A.chk = cv.take<int32_t>(n_edges_total);
   A.explored = explored; A.n_explored = n_explored; A.prev = prev; A.elist = explored_edges; A.n_elist = n_explored_edges;
-  A.n_checks = n_checks; A.n_spec = n_spec_checks; A.status = status; A.path = path; A.path_len = path_len;
+  A.n_checks = n_checks; A.n_spec = n_spec_checks; A.status = status; A.path = path; A.path_len = path_len; A.path_cost = path_cost;
   A.cap_nodes = cap_nodes; A.cap_elist = cap_explored_edges;
   maze_tree_search_kernel<<<(unsigned)n_graphs, kSearchThreads, 0, static_cast<cudaStream_t>(stream)>>>(A);
+  GMP_LAUNCH_CHECK();
+  return GMP_OK;
+}
+
+extern "C" int gmp_search_result_rows(const int32_t* status, const float* path_cost, const int32_t* n_checks, const int32_t* n_spec_checks,
+                                      const int32_t* n_explored, int64_t n_problems, int32_t first_problem_id, float* rows_out, void* stream) {
+  GMP_REQUIRE(n_problems >= 0, "n_problems < 0");
+  if (n_problems == 0) return GMP_OK;
+  GMP_REQUIRE(status && n_checks && n_spec_checks && n_explored && rows_out, "null pointer");
+  search_rows_kernel<<<(unsigned)((n_problems + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      status, path_cost, n_checks, n_spec_checks, n_explored, first_problem_id, (int)n_problems, rows_out);
   GMP_LAUNCH_CHECK();
   return GMP_OK;
 }

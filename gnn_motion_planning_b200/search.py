@@ -34,6 +34,7 @@ class TreeSearchState:
         self.elist = z(n_problems, cap_explored_edges)
         self.n_explored, self.n_elist, self.n_checks, self.n_spec = z(n_problems), z(n_problems), z(n_problems), z(n_problems)
         self.status, self.path_len = z(n_problems), z(n_problems)
+        self.path_cost = torch.zeros(n_problems, dtype=torch.float32, device=device)
         self._ws = None
 
     def workspace(self, nbytes, device):
@@ -59,8 +60,19 @@ def maze_tree_search(state, v, node_ptr_d, n_free_d, edge_index, edge_ptr_d, log
         _lib.ptr(logits), _lib.ptr(goal64), _lib.ptr(maps), _lib.ptr(problem_of_graph), _lib.ptr(slot_of_graph), B, n_nodes_total,
         n_edges_total, int(spec_k), int(bool(first_round)), _lib.ptr(state.explored), _lib.ptr(state.n_explored), _lib.ptr(state.prev),
         _lib.ptr(state.elist), _lib.ptr(state.n_elist), _lib.ptr(state.n_checks), _lib.ptr(state.n_spec), _lib.ptr(state.status),
-        _lib.ptr(state.path), _lib.ptr(state.path_len), state.cap_nodes, state.cap_elist, _lib.ptr(ws), ws.numel(),
+        _lib.ptr(state.path), _lib.ptr(state.path_len), _lib.ptr(state.path_cost), state.cap_nodes, state.cap_elist, _lib.ptr(ws), ws.numel(),
         _lib.stream_ptr(v.device)))
+
+
+@torch.no_grad()
+def result_rows(state, first_problem_id=0):
+    """[S,6] f32 rows (problem id, success, path cost, search checks, uncommitted speculative checks, explored nodes): the
+    per-problem tuple of eval_gnn.py:120-134 and the payload of the multi-GPU all-gather."""
+    rows = torch.empty((state.S, 6), dtype=torch.float32, device=state.status.device)
+    _lib.check(_lib.load().gmp_search_result_rows(_lib.ptr(state.status), _lib.ptr(state.path_cost), _lib.ptr(state.n_checks),
+                                                  _lib.ptr(state.n_spec), _lib.ptr(state.n_explored), state.S, int(first_problem_id),
+                                                  _lib.ptr(rows), _lib.stream_ptr(state.status.device)))
+    return rows
 
 
 def _sample_batch(rngs, need, maps_d, problem_ids, device):
@@ -171,6 +183,7 @@ def explore_batch(model, maps, init_states, goal_states, problem_ids, seeds, bat
         active = nxt
     # ---- results
     status = st.status.cpu().numpy()
+    rows = result_rows(st).cpu().numpy()
     n_expl, n_chk, n_spec, plen = (t.cpu().numpy() for t in (st.n_explored, st.n_checks, st.n_spec, st.path_len))
     explored, path = st.explored.cpu().numpy(), st.path.cpu().numpy()
     out = []
@@ -179,7 +192,7 @@ def explore_batch(model, maps, init_states, goal_states, problem_ids, seeds, bat
         nodes = path[p, :plen[p]].tolist() if ok else []
         out.append(dict(success=bool(ok), path_nodes=nodes, path=[last_v[p][i] for i in nodes], explored=explored[p, :n_expl[p]].tolist(),
                         c_explore=int(c_sample[p] + n_chk[p]), c_search=int(n_chk[p]), spec_checks=int(n_spec[p]), n_nodes=len(last_v[p]),
-                        rounds=int(rounds[p])))
+                        rounds=int(rounds[p]), path_cost=float(rows[p, 2]), row=rows[p]))
     return out
 
 

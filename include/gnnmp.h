@@ -151,7 +151,8 @@ int gmp_maze_edge_fp_graph(const float* v, const int64_t* edge_index, int64_t ed
  *   persistent state, S rows: explored [S,cap_nodes], n_explored [S], prev [S,cap_nodes], explored_edges [S,cap_explored_edges]
  *   (the flat list of eval_gnn.py:184,214), n_explored_edges [S], n_checks [S] (collision_check_count increments of the search:
  *   edge checks + the in_goal_region state checks), n_spec_checks [S] (speculative checks never committed), status [S],
- *   path [S,cap_nodes] + path_len [S] (node ids from 0 to the goal-region node, eval_gnn.py:223-229). */
+ *   path [S,cap_nodes] + path_len [S] (node ids from 0 to the goal-region node, eval_gnn.py:223-229), path_cost [S] f32 (nullable;
+ *   path_cost(path), eval_gnn.py:53-58). */
 int64_t gmp_tree_search_workspace_bytes(int64_t n_graphs, int64_t n_nodes_total, int64_t n_edges_total);
 int gmp_maze_tree_search(const float* v, const int32_t* node_ptr, const int32_t* n_free, const int64_t* edge_index,
                          int64_t edge_row_stride, const int32_t* edge_ptr, const float* edge_logits, const double* goal,
@@ -159,8 +160,13 @@ int gmp_maze_tree_search(const float* v, const int32_t* node_ptr, const int32_t*
                          int64_t n_graphs, int64_t n_nodes_total, int64_t n_edges_total, int spec_k, int first_round,
                          int32_t* explored, int32_t* n_explored, int32_t* prev, int32_t* explored_edges,
                          int32_t* n_explored_edges, int32_t* n_checks, int32_t* n_spec_checks, int32_t* status,
-                         int32_t* path, int32_t* path_len, int32_t cap_nodes, int32_t cap_explored_edges,
+                         int32_t* path, int32_t* path_len, float* path_cost, int32_t cap_nodes, int32_t cap_explored_edges,
                          void* workspace, int64_t workspace_bytes, void* stream);
+/* The per-problem tuple the reference reduces at the end of eval_gnn (eval_gnn.py:120-134), as rows of 6 floats:
+ * (first_problem_id + i, success, path_cost, n_checks, n_spec_checks, n_explored).  These rows are what the multi-GPU run
+ * all-gathers (NCCL, host side). */
+int gmp_search_result_rows(const int32_t* status, const float* path_cost, const int32_t* n_checks, const int32_t* n_spec_checks,
+                           const int32_t* n_explored, int64_t n_problems, int32_t first_problem_id, float* rows_out, void* stream);
 
 /* ---- arm collision: KukaEnv / Kuka2Env (environment/kuka_env.py, kuka_2arm_env.py) ------------- */
 /* The reference queries PyBullet contact points; this library substitutes its own geometric model (DESIGN.md:

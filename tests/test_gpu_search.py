@@ -27,7 +27,7 @@ def _rows(mp, pids):
 
 @pytest.mark.parametrize("spec_k", [1, 8])
 def test_c1_batch_matches_reference(cuda_device, setup, spec_k):
-    from gnn_motion_planning_b200.search import explore_batch
+    from gnn_motion_planning_b200.search import explore_batch, path_cost
     mp, model = setup
     gold = np.load(os.path.join(G, "explore_c1.npz"))
     pids = [int(p) for p in gold["ids"]]
@@ -40,6 +40,8 @@ def test_c1_batch_matches_reference(cuda_device, setup, spec_k):
         assert r["explored"] == list(gold["p%d_explored" % pid]), pid             # same search order
         assert r["c_explore"] == int(gold["p%d_c_explore" % pid]), pid            # same collision_check_count
         assert np.allclose(np.array(r["path"]), gold["p%d_path" % pid]), pid
+        assert abs(r["path_cost"] - path_cost(gold["p%d_path" % pid])) < 1e-5     # the device-side result row (eval_gnn.py:120-122)
+        assert r["row"][1] == 1.0 and r["row"][3] == r["c_search"] and r["row"][5] == len(r["explored"])
         assert r["rounds"] == 1
         wasted += r["spec_checks"]
     assert (wasted == 0) if spec_k == 1 else (wasted > 0)

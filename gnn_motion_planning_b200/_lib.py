@@ -8,7 +8,7 @@ import os
 from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_uint8, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgnnmp.so")
+LIB_PATH = os.environ.get("GNNMP_LIB_PATH") or os.path.join(_HERE, "libgnnmp.so")   # (override: A/B builds of the same library)
 
 GMP_DTYPE_F32 = 0
 GMP_DTYPE_F64 = 1

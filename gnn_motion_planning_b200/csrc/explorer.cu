@@ -1380,7 +1380,10 @@ int run_forward(gmp_handle* h, int64_t B, const float* v, const int64_t* edge_in
     GMP_CUDA(cudaFuncSetAttribute(edge_msg_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MsgSmem<E>::kBytes));
     GMP_CUDA(cudaFuncSetAttribute(policy_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
     if constexpr (E == 32)
-      GMP_CUDA(cudaFuncSetAttribute(edge_feature_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<C>::kSmemBytes));
+      {
+        GMP_CUDA(cudaFuncSetAttribute(edge_feature_tc_kernel<C, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<C>::kSmemBytes));
+        GMP_CUDA(cudaFuncSetAttribute(edge_feature_tc_kernel<C, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<C>::kSmemBytes));
+      }
     if constexpr (E == 64) {
       GMP_CUDA(cudaFuncSetAttribute(edge_feature64_tc_kernel<C, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tc64Cfg<C>::template smem<0>()));
       GMP_CUDA(cudaFuncSetAttribute(edge_feature64_tc_kernel<C, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tc64Cfg<C>::template smem<1>()));
@@ -1447,8 +1450,12 @@ int run_forward(gmp_handle* h, int64_t B, const float* v, const int64_t* edge_in
       tc_detail::unit_meta_kernel<<<(tile_e[B] + 255) / 256, 256, 0, st>>>(ws.tile_ptr_e, (int)B, tile_e[B], ws.edge_ptr, ws.obs_ptr,
                                                                           ws.tc_tab_off, ws.tc_unit_meta);
       GMP_LAUNCH_CHECK();
-      edge_feature_tc_kernel<C><<<std::min<int>(tile_e[B], kNumSMs), 384, TcCfg<C>::kSmemBytes, st>>>(
-          W + m.w.tc_img, v, ws.csr_src, ws.csr_dst, ws.tc_unit_meta, tile_e[B], ws.tc_tables, tc_stride, use_obstacles, ws.P, ws.Q);
+      if (m.edge_feature_mode == 2)    // round-1 organisation: four warps per tile, thread == row
+        edge_feature_tc_kernel<C, 1><<<std::min<int>(tile_e[B], kNumSMs), 384, TcCfg<C>::kSmemBytes, st>>>(
+            W + m.w.tc_img, v, ws.csr_src, ws.csr_dst, ws.tc_unit_meta, tile_e[B], ws.tc_tables, tc_stride, use_obstacles, ws.P, ws.Q);
+      else                             // eight warps per tile, columns split between warp pairs
+        edge_feature_tc_kernel<C, 2><<<std::min<int>(tile_e[B], kNumSMs), 544, TcCfg<C>::kSmemBytes, st>>>(
+            W + m.w.tc_img, v, ws.csr_src, ws.csr_dst, ws.tc_unit_meta, tile_e[B], ws.tc_tables, tc_stride, use_obstacles, ws.P, ws.Q);
       GMP_LAUNCH_CHECK();
       tc_done = true;
     }
@@ -1584,7 +1591,7 @@ extern "C" int gmp_explorer_set_tensor(gmp_handle* h, const char* name, const fl
 
 extern "C" int gmp_explorer_set_edge_feature_mode(gmp_handle* h, int mode) {
   GMP_REQUIRE(h, "null handle");
-  GMP_REQUIRE(mode >= -1 && mode <= 1, "mode: -1 auto, 0 fp32 SIMT, 1 tcgen05 3xTF32");
+  GMP_REQUIRE(mode >= -1 && mode <= 2, "mode: -1 auto, 0 fp32 SIMT, 1 tcgen05 3xTF32, 2 tcgen05 with the round-1 four-warp tiles");
   h->ex.edge_feature_mode = mode;
   return GMP_OK;
 }

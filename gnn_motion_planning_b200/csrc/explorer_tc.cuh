@@ -153,8 +153,15 @@ __device__ __forceinline__ void layernorm_row(float* x, const float* __restrict_
 
 }  // namespace tc_detail
 
-template <int C>
-__global__ void __launch_bounds__(384, 1) edge_feature_tc_kernel(
+// HALVES = 1: four warps per tile, thread == row (the round-1 organisation, 384 threads).
+// HALVES = 2: EIGHT warps per tile: warps w and w + 8 own the same 32 TMEM lanes (rows) and each take half of the columns of
+//             every vector (16 of the 32 features, every other 16-column piece of the scores); row-wise reductions (self score,
+//             softmax maximum and sum, LayerNorm moments) are completed by exchanging one float per row through shared memory
+//             under a 64-thread named barrier.  The softmax is rolled over 16-column pieces in two passes (maximum, then
+//             exponentials) -- no 96-entry register array -- so a thread fits in 120 registers and FOUR epilogue warps share
+//             each scheduler instead of two (round 1: issue slots 35 % busy, epilogues 81 % of a tile's time).  544 threads.
+template <int C, int HALVES>
+__global__ void __launch_bounds__(HALVES == 1 ? 384 : 544, 1) edge_feature_tc_kernel(
     const float* __restrict__ tcw, const float* __restrict__ v, const int32_t* __restrict__ csr_src,
     const int32_t* __restrict__ csr_dst, const int4* __restrict__ unit_meta, int n_units, const float* __restrict__ tc_tables,
     int64_t tc_tab_stride, int use_obstacles, float* __restrict__ P, float* __restrict__ Q) {
@@ -165,6 +172,8 @@ __global__ void __launch_bounds__(384, 1) edge_feature_tc_kernel(
   float* tabbuf = smem_tc + Cf::kImage;
   __shared__ uint64_t bar_ready[2], bar_done[2], bar_tabfull;
   __shared__ uint32_t tmem_slot;
+  __shared__ float xch[HALVES == 2 ? 2 * 2 * 2 * 128 : 1];                    // [tile][parity][half][row]: row-reduction exchange
+  constexpr int kIssuer = 8 * HALVES;                                          // warp index of the MMA issuer
 
   const int warp_u = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
   // ---- one-time setup: weights -> shared memory, barriers, TMEM
@@ -174,11 +183,11 @@ __global__ void __launch_bounds__(384, 1) edge_feature_tc_kernel(
     for (int i = threadIdx.x; i < Cf::kImage / 4; i += blockDim.x) d4[i] = __ldg(s4 + i);
   }
   if (threadIdx.x == 0) {
-    mbar_init(&bar_ready[0], 128); mbar_init(&bar_ready[1], 128);
+    mbar_init(&bar_ready[0], 128 * HALVES); mbar_init(&bar_ready[1], 128 * HALVES);
     mbar_init(&bar_done[0], 1); mbar_init(&bar_done[1], 1);
     mbar_init(&bar_tabfull, 1);
   }
-  if (warp_u == 8) umma::tmem_alloc(&tmem_slot, 512);
+  if (warp_u == kIssuer) umma::tmem_alloc(&tmem_slot, 512);
   umma::fence_proxy_async();
   umma::fence_before_sync();
   __syncthreads();
@@ -186,15 +195,17 @@ __global__ void __launch_bounds__(384, 1) edge_feature_tc_kernel(
   const uint32_t tm = tmem_slot;
   const int n_blocks = use_obstacles ? 3 : 0;
 
-  if (warp_u >= 8) {
-    // warpgroup 2 hands most of its registers to the two compute warpgroups (per SM sub-partition: 2 x 224 + 56 <= 512)
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-  } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+  if constexpr (HALVES == 1) {
+    if (warp_u >= 8) {
+      // warpgroup 2 hands most of its registers to the two compute warpgroups (per SM sub-partition: 2 x 224 + 56 <= 512)
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    } else {
+      asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    }
   }
-  if (warp_u > 8) {
-    // warps 9-11 only pad the issuer's warpgroup
-  } else if (warp_u == 8) {
+  if (warp_u > kIssuer) {
+    // warps 9-11 only pad the issuer's warpgroup (HALVES == 1)
+  } else if (warp_u == kIssuer) {
     // =================================================================== MMA issuer / table loader
     const uint32_t tm_u = __shfl_sync(0xffffffffu, tm, 0);
     const uint32_t img_s = smem_u32(img), tab_s = smem_u32(tabbuf);
@@ -360,7 +371,7 @@ __global__ void __launch_bounds__(384, 1) edge_feature_tc_kernel(
              "GV+scores %lld PV %lld QP %lld\n", clock64() - prof_t0, prof_ready[0], prof_ready[1], prof_tab, prof_issue[0],
              prof_issue[1], prof_issue[2], prof_issue[3], prof_issue[4]);
 #endif
-  } else {
+  } else if constexpr (HALVES == 1) {
     // =================================================================== compute warps: thread == edge row
     const int tile = warp_u >> 2;
     const int row = threadIdx.x & 127;
@@ -623,10 +634,325 @@ __global__ void __launch_bounds__(384, 1) edge_feature_tc_kernel(
              (n_units + gridDim.x - 1) / gridDim.x, prof_w[0], prof_e[0], prof_w[1], prof_e[1], prof_w[2], prof_e[2], prof_w[3], prof_e[3],
              prof_w[4], prof_e[4], prof_w[5], prof_e[5]);
 #endif
+  } else {
+    // =================================================================== compute warps, column-split (HALVES == 2)
+    const int qd = warp_u & 3, tile = (warp_u >> 2) & 1, half = warp_u >> 3;
+    const int row = qd * 32 + (int)(threadIdx.x & 31);
+    const uint32_t tc = tm + ((uint32_t)(qd * 32) << 16) + (uint32_t)tile * 256u;
+    const float* vec = img + Cf::VEC;
+    constexpr int H = E / 2;
+    const int c0 = half * H;                               // this thread's 16 of the 32 features
+    uint32_t dph = 0;
+    int par = 0;
+    float* xme = xch + tile * 512 + half * 128 + row;      // + par * 256;  the partner's slot is at (half ^ 1)
+    const float* xot = xch + tile * 512 + (half ^ 1) * 128 + row;
+    const int bar_id = 1 + tile * 4 + qd;                  // named barrier of this (tile, lane quarter): the two warps that share rows
+#ifdef GMP_TC_PROFILE
+    long long* prof_xp = nullptr;
+    auto pair_sync = [&]() { const long long t0 = clock64(); asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory"); if (prof_xp) *prof_xp += clock64() - t0; };
+#else
+    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory"); };
+#endif
+    // complete a row reduction: returns (half 0 part) + (half 1 part) -- the same expression in both warps
+    auto xsum = [&](float mine) -> float {
+      xme[par * 256] = mine;
+      pair_sync();
+      const float other = xot[par * 256];
+      par ^= 1;
+      return half == 0 ? mine + other : other + mine;
+    };
+    auto xmax = [&](float mine) -> float {
+      xme[par * 256] = mine;
+      pair_sync();
+      const float other = xot[par * 256];
+      par ^= 1;
+      return fmaxf(mine, other);
+    };
+    auto publish = [&]() {
+      umma::wait_st();
+      umma::fence_before_sync();
+      umma::mbar_arrive(&bar_ready[tile]);
+    };
+#ifdef GMP_TC_PROFILE
+    long long prof_w[6] = {0, 0, 0, 0, 0, 0}, prof_e[6] = {0, 0, 0, 0, 0, 0}, prof_x = 0, prof_last = clock64(), prof_t0 = prof_last;
+    long long prof_q[4] = {0, 0, 0, 0};   // w_1 epilogue split: tcgen05.ld + wait | math + tcgen05.st issue | wait::st | fence + arrive
+    int prof_kind = 5;
+#endif
+    auto await = [&](int kind = 5) {   // kind (profiling only): 0 Gx|Vx+scores, 1 P.V, 2 w_1, 3 w_2, 4 tail, 5 encoders / other
+#ifdef GMP_TC_PROFILE
+      const long long w0 = clock64();
+      prof_e[prof_kind] += w0 - prof_last;   // work since the previous await belongs to that stage's epilogue
+#endif
+      umma::mbar_wait_guard(&bar_done[tile], dph);
+      dph ^= 1u;
+      umma::fence_after_sync();
+#ifdef GMP_TC_PROFILE
+      prof_last = clock64();
+      prof_w[kind] += prof_last - w0;
+      prof_kind = kind;
+#endif
+    };
+    // LayerNorm of a row whose 32 features are split over the two warps (biased variance, two passes)
+    auto layernorm_half = [&](float* y, const float* gamma, const float* beta) {
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+      for (int n = 0; n < H; n += 4) { s0 += y[n]; s1 += y[n + 1]; s2 += y[n + 2]; s3 += y[n + 3]; }
+      const float mu = xsum((s0 + s1) + (s2 + s3)) * (1.0f / E);
+      float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+#pragma unroll
+      for (int n = 0; n < H; n += 4) {
+        const float d0 = y[n] - mu, d1 = y[n + 1] - mu, d2 = y[n + 2] - mu, d3 = y[n + 3] - mu;
+        v0 = fmaf(d0, d0, v0); v1 = fmaf(d1, d1, v1); v2 = fmaf(d2, d2, v2); v3 = fmaf(d3, d3, v3);
+      }
+      const float var = xsum((v0 + v1) + (v2 + v3)) * (1.0f / E);
+      const float rstd = 1.0f / sqrtf(var + 1e-6f);
+#pragma unroll
+      for (int n = 0; n < H; ++n) y[n] = (y[n] - mu) * rstd * gamma[c0 + n] + beta[c0 + n];
+    };
+#ifdef GMP_TC_PROFILE
+    prof_xp = &prof_x;
+#endif
+    auto load_meta = [&](int u) { return u < n_units ? __ldg(unit_meta + u) : make_int4(0, 0, 0, 0); };
+    int4 meta_nx = load_meta(blockIdx.x), meta_nx2 = load_meta(blockIdx.x + gridDim.x);
+    int s_nx = 0, d_nx = 0;
+    auto load_endpoints = [&](const int4 mm) {
+      const int sl = mm.x + tile * 128 + row;
+      const bool ok = sl < mm.y;
+      s_nx = ok ? __ldg(csr_src + sl) : 0;
+      d_nx = ok ? __ldg(csr_dst + sl) : 0;
+    };
+    load_endpoints(meta_nx);
+    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+      const int4 meta = meta_nx;
+      const int slot = meta.x + tile * 128 + row;
+      const bool valid = slot < meta.y;
+      const int O = meta.z;
+      const int nch = n_blocks ? tc_nchunks(O) : 0, per = tc_per(O, nch);
+      const int s_node = s_nx, d_node = d_nx;
+      meta_nx = meta_nx2;
+      load_endpoints(meta_nx);
+      meta_nx2 = load_meta(unit + 2 * gridDim.x);
+      auto gather = [&](float* in) {   // cat(v[src], v[dst]), zero padded to K0
+#pragma unroll
+        for (int k = 0; k < K0; ++k) in[k] = 0.f;
+#pragma unroll
+        for (int k = 0; k < C; ++k) {
+          in[k] = __ldg(v + (size_t)s_node * C + k);
+          in[C + k] = __ldg(v + (size_t)d_node * C + k);
+        }
+      };
+      // this thread's half of hidden = relu(W in + b) of encoder `which` (0 edge_free_code.0, 1 edge_code.0), plain FMAs
+      auto simt_hidden = [&](const float* in, int which, float* h) {
+        const float* Wf = img + Cf::ENC0F + which * 32 * Cf::K4;
+        const float* bb = vec + (which ? Cf::vEC0b : Cf::vEF0b);
+#pragma unroll
+        for (int n = 0; n < H; ++n) {
+          float a = bb[c0 + n];
+#pragma unroll
+          for (int k4 = 0; k4 < Cf::K4; k4 += 4) {
+            const float4 w = *reinterpret_cast<const float4*>(Wf + (c0 + n) * Cf::K4 + k4);
+            a = fmaf(w.x, in[k4], a); a = fmaf(w.y, in[k4 + 1], a); a = fmaf(w.z, in[k4 + 2], a); a = fmaf(w.w, in[k4 + 3], a);
+          }
+          h[n] = fmaxf(a, 0.f);
+        }
+      };
+      auto stage_edge_code = [&]() {
+        float in[K0];
+        gather(in);
+        if constexpr (Cf::kSimtIn) {
+          float h[H];
+          simt_hidden(in, 1, h);
+          umma::st_split<H>(tc + Cf::cHH + c0, tc + Cf::cHL + c0, h);
+        } else {
+          umma::st_split<K0 / 2>(tc + Cf::cHH + half * (K0 / 2), tc + Cf::cHL + half * (K0 / 2), in + half * (K0 / 2));
+        }
+      };
+      float x[H];
+      // ---- edge_free_code                                                  (model.py:123)
+      {
+        float in[K0];
+        gather(in);
+        if constexpr (Cf::kSimtIn) {
+          simt_hidden(in, 0, x);
+        } else {
+          umma::st_split<K0 / 2>(tc + Cf::cXH + half * (K0 / 2), tc + Cf::cXL + half * (K0 / 2), in + half * (K0 / 2));
+          publish();
+          await();
+          umma::ld16(tc + Cf::cA1 + c0, x);
+          umma::wait_ld();
+#pragma unroll
+          for (int n = 0; n < H; ++n) x[n] = fmaxf(x[n] + vec[Cf::vEF0b + c0 + n], 0.f);
+        }
+      }
+      umma::st_split<H>(tc + Cf::cXH + c0, tc + Cf::cXL + c0, x);
+      publish();
+      await();
+      umma::ld16(tc + Cf::cA1 + c0, x);
+      umma::wait_ld();
+#pragma unroll
+      for (int n = 0; n < H; ++n) x[n] += vec[Cf::vEF2b + c0 + n];
+      umma::st_split<H>(tc + Cf::cXH + c0, tc + Cf::cXL + c0, x);
+      if (n_blocks == 0) stage_edge_code();
+      publish();
+      // ---- three edge Blocks                                               (model.py:130, 153-218)
+      for (int blk = 0; blk < n_blocks; ++blk) {
+        const float* bv = vec + Cf::vBLK + blk * 192;
+        float acc[H];
+        float m, l = 1.0f;
+        await(0);   // Gx | Vx (+ scores of the first one or two sub-chunks)
+        {
+          float u[H];
+          umma::ld16(tc + Cf::cA1 + c0, u);
+          umma::ld16(tc + Cf::cA1 + 32 + c0, acc);          // value of the row itself, weight exp2(s_self - m) = 1
+          umma::wait_ld();
+          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;     // self score x^T G x   (model.py:175,177)
+#pragma unroll
+          for (int n = 0; n < H; n += 4) {
+            s0 = fmaf(u[n], x[n], s0); s1 = fmaf(u[n + 1], x[n + 1], s1); s2 = fmaf(u[n + 2], x[n + 2], s2); s3 = fmaf(u[n + 3], x[n + 3], s3);
+          }
+          m = xsum((s0 + s1) + (s2 + s3));
+        }
+        // online softmax over one sub-chunk, two rolled passes over this warp's 16-column pieces (pieces half, half + 2, ...):
+        // scores at TMEM column `col` -> probabilities (hi plane in place, lo plane at cPL); returns the rescale factor
+        auto softmax_sub = [&](uint32_t col, int cnt) -> float {
+          float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+          for (int j = half * 16; j < per; j += 32) {
+            float sc[16];
+            umma::ld16(tc + col + j, sc);
+            umma::wait_ld();
+            if (j + 16 > cnt) {                           // padded table rows score 0: weight 0
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (j + i >= cnt) sc[i] = -INFINITY;
+            }
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              mx0 = fmaxf(mx0, sc[i]); mx1 = fmaxf(mx1, sc[i + 1]); mx2 = fmaxf(mx2, sc[i + 2]); mx3 = fmaxf(mx3, sc[i + 3]);
+            }
+          }
+          const float mnew = fmaxf(m, xmax(fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3))));
+          const float corr = umma::ex2_approx(m - mnew);
+          float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+          for (int j = half * 16; j < per; j += 32) {
+            float sc[16];
+            umma::ld16(tc + col + j, sc);
+            umma::wait_ld();
+            if (j + 16 > cnt) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (j + i >= cnt) sc[i] = -INFINITY;
+            }
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              const float p0 = umma::ex2_approx(sc[i] - mnew), p1 = umma::ex2_approx(sc[i + 1] - mnew),
+                          p2 = umma::ex2_approx(sc[i + 2] - mnew), p3 = umma::ex2_approx(sc[i + 3] - mnew);
+              l0 += p0; l1 += p1; l2 += p2; l3 += p3;
+              sc[i] = p0; sc[i + 1] = p1; sc[i + 2] = p2; sc[i + 3] = p3;
+            }
+            umma::st_split<16>(tc + col + j, tc + Cf::cPL + j, sc);
+          }
+          l = fmaf(l, corr, xsum((l0 + l1) + (l2 + l3)));
+          m = mnew;
+          return corr;
+        };
+        for (int s2 = 0; 2 * s2 < nch; ++s2) {
+          const int ns = min(2, nch - 2 * s2);
+          if (s2 > 0) {
+            // (> 128 obstacles) the probabilities' lo plane overwrote XH / XL: restore the A operand for these scores
+            umma::st_split<H>(tc + Cf::cXH + c0, tc + Cf::cXL + c0, x);
+            publish();
+            await();
+          }
+          for (int sub = 0; sub < ns; ++sub) {
+            const float corr = softmax_sub(sub ? Cf::cSC1 : Cf::cSC, max(0, min(per, O - (2 * s2 + sub) * per)));
+            publish();   // -> P.V of this sub-chunk
+            await(1);
+            float pv[H];
+            umma::ld16(tc + (ns == 2 ? Cf::cPV2 : Cf::cPV1) + c0, pv);
+            umma::wait_ld();
+#pragma unroll
+            for (int n = 0; n < H; ++n) acc[n] = fmaf(acc[n], corr, pv[n]);
+          }
+        }
+        // softmax normalisation, residual, attention.layer_norm               (model.py:181)
+        {
+          const float inv = 1.0f / l;
+#pragma unroll
+          for (int n = 0; n < H; ++n) acc[n] = fmaf(acc[n], inv, x[n]);
+        }
+        layernorm_half(acc, bv, bv + 32);
+        umma::st_split<H>(tc + Cf::cXH + c0, tc + Cf::cXL + c0, acc);
+        publish();
+        await(2);   // map_feed.w_1                                             (model.py:193-201)
+#ifdef GMP_TC_PROFILE
+        const long long q0 = clock64();
+#endif
+        umma::ld16(tc + Cf::cA1 + c0, x);
+        umma::wait_ld();
+#ifdef GMP_TC_PROFILE
+        const long long q1 = clock64();
+#endif
+#pragma unroll
+        for (int n = 0; n < H; ++n) x[n] = fmaxf(x[n] + bv[64 + c0 + n], 0.f);
+        umma::st_split<H>(tc + Cf::cXH + c0, tc + Cf::cXL + c0, x);
+#ifdef GMP_TC_PROFILE
+        const long long q2 = clock64();
+        umma::wait_st();
+        const long long q3 = clock64();
+#endif
+        publish();
+#ifdef GMP_TC_PROFILE
+        prof_q[0] += q1 - q0; prof_q[1] += q2 - q1; prof_q[2] += q3 - q2; prof_q[3] += clock64() - q3;
+#endif
+        await(3);   // map_feed.w_2
+        umma::ld16(tc + Cf::cA1 + c0, x);
+        umma::wait_ld();
+#pragma unroll
+        for (int n = 0; n < H; ++n) x[n] += bv[96 + c0 + n] + acc[n];
+        layernorm_half(x, bv + 128, bv + 160);
+        umma::st_split<H>(tc + Cf::cXH + c0, tc + Cf::cXL + c0, x);
+        if (blk == n_blocks - 1) stage_edge_code();
+        publish();
+      }
+      // ---- hidden layer of edge_code on the tensor cores (wide inputs)     (model.py:120)
+      if constexpr (!Cf::kSimtIn) {
+        await();
+        float h[H];
+        umma::ld16(tc + Cf::cSC + c0, h);
+        umma::wait_ld();
+#pragma unroll
+        for (int n = 0; n < H; ++n) h[n] = fmaxf(h[n] + vec[Cf::vEC0b + c0 + n], 0.f);
+        umma::st_split<H>(tc + Cf::cHH + c0, tc + Cf::cHL + c0, h);
+        publish();
+      }
+      // ---- Q = Wc ef + b (model.py:145-146);  P = W4 ef + W5 edge_code + b (model.py:39), edge_code.2 folded into W5
+      await(4);
+      float q[H];
+      umma::ld16(tc + Cf::cA1 + c0, q);
+      umma::ld16(tc + Cf::cA1 + 32 + c0, x);
+      umma::wait_ld();
+      if (valid) {
+        float4* q4 = reinterpret_cast<float4*>(Q + (size_t)slot * E + c0);
+        float4* p4 = reinterpret_cast<float4*>(P + (size_t)slot * E + c0);
+#pragma unroll
+        for (int n = 0; n < H; n += 4) {
+          q4[n >> 2] = make_float4(q[n] + vec[Cf::vQb + c0 + n], q[n + 1] + vec[Cf::vQb + c0 + n + 1], q[n + 2] + vec[Cf::vQb + c0 + n + 2],
+                                   q[n + 3] + vec[Cf::vQb + c0 + n + 3]);
+          p4[n >> 2] = make_float4(x[n] + vec[Cf::vPb + c0 + n], x[n + 1] + vec[Cf::vPb + c0 + n + 1], x[n + 2] + vec[Cf::vPb + c0 + n + 2],
+                                   x[n + 3] + vec[Cf::vPb + c0 + n + 3]);
+        }
+      }
+    }
+#ifdef GMP_TC_PROFILE
+    if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && qd == 0)
+      printf("tc8 profile: tile %d half %d total %lld cyc (%d units), pair barriers %lld; wait/epilogue per stage kind: A %lld/%lld PV %lld/%lld "
+             "w1 %lld/%lld w2 %lld/%lld tail %lld/%lld enc %lld/%lld; w1 epilogue: ld %lld math+st %lld wait_st %lld arrive %lld\n", tile, half, clock64() - prof_t0, (n_units + gridDim.x - 1) / gridDim.x, prof_x,
+             prof_w[0], prof_e[0], prof_w[1], prof_e[1], prof_w[2], prof_e[2], prof_w[3], prof_e[3], prof_w[4], prof_e[4], prof_w[5], prof_e[5], prof_q[0], prof_q[1], prof_q[2], prof_q[3]);
+#endif
   }
   umma::fence_before_sync();
   __syncthreads();
-  if (warp_u == 8) umma::tmem_dealloc(tm, 512);
+  if (warp_u == kIssuer) umma::tmem_dealloc(tm, 512);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -61,7 +61,8 @@ int gmp_explorer_set_tensor(gmp_handle* h, const char* name, const float* data_h
 int gmp_explorer_finalize(gmp_handle* h);
 /* Arithmetic of the edge-feature stage (edge encoders + edge Blocks, model.py:120,123,130):
  *   -1 auto (default) / 1: tcgen05 tensor cores with 3xTF32 split operands (embed_size 64: graphs with more than 32
- *    obstacles fall back to fp32 FMA for the edge-feature stage);  0: fp32 FMA (SIMT) always.
+ *    obstacles fall back to fp32 FMA for the edge-feature stage);  0: fp32 FMA (SIMT) always;  2: tensor cores with the
+ *    round-1 tile organisation of the embed-32 kernel (four epilogue warps per tile instead of eight).
  * Both meet the 1e-4 logit tolerance; the switch exists for A/B parity tests and profiling. */
 int gmp_explorer_set_edge_feature_mode(gmp_handle* h, int mode);
 

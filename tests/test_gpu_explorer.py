@@ -150,7 +150,8 @@ def test_tensor_core_edge_stage_vs_simt_and_oracle(cuda_device, tag, wfile, dims
     GOAL = torch.from_numpy(np.stack([g[2] for g in graphs])).to(cuda_device)
     OBS = torch.from_numpy(np.concatenate([g[3] for g in graphs])).to(cuda_device)
     out = {}
-    for mode in ("tc", "simt"):
+    modes = ("tc", "simt", "tc4") if dims[2] == 32 else ("tc", "simt")
+    for mode in modes:
         m.set_edge_feature_mode(mode)
         out[mode] = m.forward_batch(V, EI, GOAL, OBS, node_ptr, edge_ptr, obs_ptr, loop=5).cpu().numpy()
     m.use_obstacles = False
@@ -163,7 +164,7 @@ def test_tensor_core_edge_stage_vs_simt_and_oracle(cuda_device, tag, wfile, dims
     for g, (v, ei, goal, obs) in enumerate(graphs):
         want = o_explorer.explorer_forward(sd, torch.from_numpy(v), torch.from_numpy(ei), torch.from_numpy(goal),
                                            torch.from_numpy(obs), loop=5, dense=False, dtype=torch.float64).numpy()
-        for mode in ("tc", "simt"):
+        for mode in modes:
             err = np.abs(out[mode][edge_ptr[g]:edge_ptr[g + 1]] - want).max()
             worst = max(worst, err)
             assert err < TOL, (tag, g, mode, err)

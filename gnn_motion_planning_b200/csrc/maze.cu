@@ -414,6 +414,70 @@ __global__ void __launch_bounds__(kSearchThreads) maze_tree_search_kernel(Search
   (void)n_spec;
 }
 
+// =====================================================================================================================
+// Steering rounds of the smoother's caller on the device: proposed_path_smootherv2               (smoother.py:194-216)
+// =====================================================================================================================
+// One thread per path (the sweep over waypoints is sequential: waypoint i is checked against the ALREADY UPDATED i-1 and the
+// not yet updated i+1, so the reference's `next_path = deepcopy(path)` sweep equals an in-place sweep).  float32 arithmetic
+// exactly as NumPy evaluates it on the float32 paths the reference holds: norm = sqrt(dx*dx + dy*dy) without FMA, ratio =
+// float32(RRT_EPS) / dist, interpolate = from + diff * ratio (maze_env.py:151-172), `dist < RRT_EPS` and `diff < 1e-5` compared
+// in float32 (NumPy 2 weak scalars).  collision_check_count increments are returned per path.
+__device__ __forceinline__ float norm2_f32(float dx, float dy) { return __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy))); }
+
+__global__ void __launch_bounds__(32) maze_steer_kernel(const float* __restrict__ old_path, const float* __restrict__ new_path,
+                                                        const int32_t* __restrict__ path_ptr, const uint8_t* __restrict__ maps,
+                                                        const int32_t* __restrict__ problem_of_path, int n_paths, float rrt_eps,
+                                                        float* __restrict__ path_out, int32_t* __restrict__ n_checks_out,
+                                                        int32_t* __restrict__ n_rounds_out, float* __restrict__ cost_out) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_paths) return;
+  const int p0 = path_ptr[g], P = path_ptr[g + 1] - p0;
+  const uint8_t* map = maps + (int64_t)(problem_of_path ? problem_of_path[g] : g) * (kW * kW);
+  const float2* oldp = reinterpret_cast<const float2*>(old_path) + p0;
+  const float2* newp = reinterpret_cast<const float2*>(new_path) + p0;
+  float2* path = reinterpret_cast<float2*>(path_out) + p0;
+  float kmax = 0.f;                                    // K = ceil(max ||old - new|| / RRT_EPS)   (:195)
+  for (int i = 0; i < P; ++i) {
+    const float2 a = oldp[i], b = newp[i];
+    path[i] = a;                                       // path = deepcopy(old_path)
+    kmax = fmaxf(kmax, __fdiv_rn(norm2_f32(a.x - b.x, a.y - b.y), rrt_eps));
+  }
+  const int K = (int)ceilf(kmax);
+  int checks = 0, rounds = 0;
+  for (int r = 0; r < K; ++r) {
+    float diff = 0.f;
+    ++rounds;
+    for (int i = 1; i + 1 < P; ++i) {
+      const float2 old_n = path[i], new_n = newp[i];
+      const float dist = norm2_f32(old_n.x - new_n.x, old_n.y - new_n.y);
+      float2 cand;
+      if (dist < rrt_eps) cand = new_n;
+      else {
+        const float ratio = __fdiv_rn(rrt_eps, dist);
+        cand.x = __fadd_rn(old_n.x, __fmul_rn(new_n.x - old_n.x, ratio));
+        cand.y = __fadd_rn(old_n.y, __fmul_rn(new_n.y - old_n.y, ratio));
+      }
+      const float2 pl = path[i - 1], pr = path[i + 1];
+      int c1 = 0, c2 = 0;
+      bool ok = edge_free<float>(map, pl.x, pl.y, cand.x, cand.y, c1);          // env._edge_fp(next_path[i-1], next_path[i])
+      if (ok) ok = edge_free<float>(map, pr.x, pr.y, cand.x, cand.y, c2);       // and env._edge_fp(next_path[i+1], next_path[i])
+      checks += c1 + c2;
+      if (ok) {
+        path[i] = cand;
+        diff = __fadd_rn(diff, norm2_f32(cand.x - new_n.x, cand.y - new_n.y));
+      }
+    }
+    if (diff < 1e-5f) break;
+  }
+  n_checks_out[g] = checks;
+  if (n_rounds_out) n_rounds_out[g] = rounds;
+  if (cost_out) {                                      // path_cost (eval_gnn.py:53-58), float32 accumulation
+    float c = 0.f;
+    for (int i = 0; i + 1 < P; ++i) c = __fadd_rn(c, norm2_f32(path[i + 1].x - path[i].x, path[i + 1].y - path[i].y));
+    cost_out[g] = c;
+  }
+}
+
 // per-problem rows of the final reduction (eval_gnn.py:120-134): (problem id, success, path cost, collision checks of the search,
 // speculative checks never committed, explored nodes) -- the payload of the multi-GPU all-gather
 __global__ void search_rows_kernel(const int32_t* __restrict__ status, const float* __restrict__ path_cost, const int32_t* __restrict__ n_checks,
@@ -545,6 +609,18 @@ extern "C" int gmp_search_result_rows(const int32_t* status, const float* path_c
   GMP_REQUIRE(status && n_checks && n_spec_checks && n_explored && rows_out, "null pointer");
   search_rows_kernel<<<(unsigned)((n_problems + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
       status, path_cost, n_checks, n_spec_checks, n_explored, first_problem_id, (int)n_problems, rows_out);
+  GMP_LAUNCH_CHECK();
+  return GMP_OK;
+}
+
+extern "C" int gmp_maze_steer_rounds(const float* old_path, const float* new_path, const int32_t* path_ptr, const uint8_t* maps,
+                                     const int32_t* problem_of_path, int64_t n_paths, double rrt_eps, float* path_out,
+                                     int32_t* n_checks_out, int32_t* n_rounds_out, float* path_cost_out, void* stream) {
+  GMP_REQUIRE(n_paths >= 0 && rrt_eps > 0, "n_paths < 0 or rrt_eps <= 0");
+  if (n_paths == 0) return GMP_OK;
+  GMP_REQUIRE(old_path && new_path && path_ptr && maps && path_out && n_checks_out, "null pointer");
+  maze_steer_kernel<<<(unsigned)((n_paths + 31) / 32), 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      old_path, new_path, path_ptr, maps, problem_of_path, (int)n_paths, (float)rrt_eps, path_out, n_checks_out, n_rounds_out, path_cost_out);
   GMP_LAUNCH_CHECK();
   return GMP_OK;
 }

@@ -79,3 +79,57 @@ def model_smooth(model, free, collided, old_path, env, iter=5):
         new_path = model(**data, loop=1).data.cpu().numpy()
         old_path = proposed_path_smootherv2(old_path, list(new_path), env)
     return old_path
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# batched, device-resident form: smoother forwards and steering rounds for MANY maze problems per launch
+@torch.no_grad()
+def steer_rounds_batch(old_path_d, new_path_d, path_ptr_d, maps_d, problem_of_path_d, rrt_eps, want_cost=False):
+    """``proposed_path_smootherv2`` (smoother.py:194-216) for a packed batch of 2-D maze paths on the device
+    (``gmp_maze_steer_rounds``): -> (path [P_total,2] f32, n_checks [B] i32, n_rounds [B] i32[, path_cost [B] f32])."""
+    from . import _lib
+    B = path_ptr_d.numel() - 1
+    dev = old_path_d.device
+    out = torch.empty_like(old_path_d)
+    checks = torch.empty(B, dtype=torch.int32, device=dev)
+    rounds = torch.empty(B, dtype=torch.int32, device=dev)
+    cost = torch.empty(B, dtype=torch.float32, device=dev) if want_cost else None
+    _lib.check(_lib.load().gmp_maze_steer_rounds(_lib.ptr(old_path_d), _lib.ptr(new_path_d), _lib.ptr(path_ptr_d), _lib.ptr(maps_d),
+                                                 _lib.ptr(problem_of_path_d), B, float(rrt_eps), _lib.ptr(out), _lib.ptr(checks),
+                                                 _lib.ptr(rounds), _lib.ptr(cost), _lib.stream_ptr(dev)))
+    return (out, checks, rounds, cost) if want_cost else (out, checks, rounds)
+
+
+@torch.no_grad()
+def model_smooth_batch(model, frees, collideds, paths, maps_d, problem_ids, rrt_eps=0.05, iter=5):
+    """``model_smooth`` (smoother.py:233-246) for many maze problems at once: per iteration ONE batched smoother forward
+    (``gmp_smoother_forward``) and ONE steering launch; paths stay on the device between iterations.
+    frees / collideds / paths: per-problem lists of states (as the reference passes them).
+    -> (list of float32 [P,2] paths, collision_check_count increments per problem [B], path costs [B])."""
+    dev = maps_d.device
+    B = len(paths)
+    P = [len(p) for p in paths]
+    path_ptr = np.concatenate([[0], np.cumsum(P)]).astype(np.int32)
+    samples, n_free = [], []
+    for f, c in zip(frees, collideds):                       # obs_data (smoother.py:52-64): pad empty lists, keep 500 + 500
+        f = list(f) if len(f) else [[0.] * 2]
+        c = list(c) if len(c) else [[0.] * 2]
+        f, c = np.asarray(f[:500], np.float32).reshape(-1, 2), np.asarray(c[:500], np.float32).reshape(-1, 2)
+        samples.append(np.concatenate([f, c]))
+        n_free.append(len(f))
+    sample_ptr = np.concatenate([[0], np.cumsum([len(x) for x in samples])]).astype(np.int32)
+    samples_d = torch.from_numpy(np.concatenate(samples)).to(dev)
+    eis = [chain_edge_index(p).numpy() for p in P]
+    edge_ptr = np.concatenate([[0], np.cumsum([e.shape[1] for e in eis])]).astype(np.int32)
+    ei_d = torch.from_numpy(np.concatenate(eis, 1)).to(dev)
+    path_d = torch.from_numpy(np.concatenate([np.asarray(p, np.float32).reshape(-1, 2) for p in paths])).to(dev)
+    path_ptr_d = torch.from_numpy(path_ptr).to(dev)
+    prob_d = torch.as_tensor(np.asarray(problem_ids, np.int32)).to(dev)
+    total = torch.zeros(B, dtype=torch.int32, device=dev)
+    cost = None
+    for _ in range(iter):
+        new_d = model.forward_batch(path_d, samples_d, ei_d, path_ptr, sample_ptr, n_free, edge_ptr, loop=1)
+        path_d, checks, _, cost = steer_rounds_batch(path_d, new_d, path_ptr_d, maps_d, prob_d, rrt_eps, want_cost=True)
+        total += checks
+    out = path_d.cpu().numpy()
+    return [out[path_ptr[i]:path_ptr[i + 1]] for i in range(B)], total.cpu().numpy(), cost.cpu().numpy()

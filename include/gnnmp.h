@@ -169,6 +169,17 @@ int gmp_maze_tree_search(const float* v, const int32_t* node_ptr, const int32_t*
 int gmp_search_result_rows(const int32_t* status, const float* path_cost, const int32_t* n_checks, const int32_t* n_spec_checks,
                            const int32_t* n_explored, int64_t n_problems, int32_t first_problem_id, float* rows_out, void* stream);
 
+/* Replaces proposed_path_smootherv2 (smoother.py:194-216) for a packed batch of 2-D maze paths: K = ceil(max ||old - new|| /
+ * rrt_eps) rounds; per round every interior waypoint is steered at most rrt_eps toward its proposal and kept iff both adjacent
+ * edges are collision free (against the already updated left neighbour); stops when the accepted waypoints have all reached
+ * their proposals.  float32 arithmetic as NumPy evaluates it on the reference's float32 paths.
+ *   old_path / new_path / path_out [P_total, 2] f32, path p owns rows path_ptr[p] .. path_ptr[p+1] (DEVICE [B+1]);
+ *   n_checks_out [B]: collision_check_count increments;  n_rounds_out [B] (nullable);  path_cost_out [B] f32 (nullable):
+ *   path_cost of the result (eval_gnn.py:53-58). */
+int gmp_maze_steer_rounds(const float* old_path, const float* new_path, const int32_t* path_ptr, const uint8_t* maps,
+                          const int32_t* problem_of_path, int64_t n_paths, double rrt_eps, float* path_out,
+                          int32_t* n_checks_out, int32_t* n_rounds_out, float* path_cost_out, void* stream);
+
 /* ---- arm collision: KukaEnv / Kuka2Env (environment/kuka_env.py, kuka_2arm_env.py) ------------- */
 /* The reference queries PyBullet contact points; this library substitutes its own geometric model (DESIGN.md:
  * FK down the URDF joint chain, link hulls filled with inscribed spheres, boxes as AABBs) -- parity with PyBullet

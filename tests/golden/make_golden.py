@@ -471,6 +471,30 @@ def more_goldens():
     mr["cases"] = np.array(cases)
     np.savez_compressed(os.path.join(HERE, "explore_rounds.npz"), **mr)
 
+    # ---------------------------------------------------------------- construct_graph (algorithm/dijkstra.py:15-31): kNN(5) + every edge checked
+    from collections import defaultdict
+    ns_c = dict(torch=torch, np=np, knn_graph=_pyg_stubs.knn_graph, coalesce=_pyg_stubs.coalesce, defaultdict=defaultdict,
+                INFINITY=float("inf"))
+    ref_functions("algorithm/dijkstra.py", ["construct_graph"], ns_c)
+    cg = {}
+    for pid in (2000, 2003):
+        np.random.seed(555 + pid)
+        env.init_new_problem(pid)
+        pts = np.array([env.init_state, env.goal_state] + list(env.sample_n_points(300)))      # float64, as the dataset builder feeds it
+        c0 = env.collision_check_count
+        edge_cost, neighbors, edge_index, edge_free = ns_c["construct_graph"](env, pts)
+        tag = "p%d" % pid
+        cg[tag + "_points"] = pts
+        cg[tag + "_edge_index"] = np.asarray(edge_index)
+        cg[tag + "_edge_free"] = np.array(edge_free)
+        cg[tag + "_checks"] = np.array(env.collision_check_count - c0)
+        cg[tag + "_cost_flat"] = np.concatenate([np.asarray(edge_cost[i], np.float64) for i in range(len(pts))])
+        cg[tag + "_nbr_flat"] = np.concatenate([np.asarray(neighbors[i], np.int64) for i in range(len(pts))])
+        cg[tag + "_deg"] = np.array([len(neighbors[i]) for i in range(len(pts))])
+        print("construct_graph", tag, np.asarray(edge_index).shape, float(np.mean(edge_free)), int(cg[tag + "_checks"]))
+    cg["ids"] = np.array([2000, 2003])
+    np.savez_compressed(os.path.join(HERE, "construct_graph.npz"), **cg)
+
 
 if __name__ == "__main__":
     if "--more-only" not in sys.argv:

@@ -113,3 +113,25 @@ def test_maze_env_protocol(cuda_device):
     # obstacles tokens as the reference builds them (maze_env.py:73-79)
     occ = np.argwhere(mp["maps"][6] == 1)
     assert np.allclose(env.obstacles, occ / 15 - 0.5)
+
+
+def test_construct_graph_golden(cuda_device):
+    """algorithm/dijkstra.py:15-31 (k-NN(5) graph + EVERY edge checked) against the reference's own construct_graph +
+    MazeEnv run on float64 points: edge list, free flags, per-node neighbour / cost lists and collision_check_count."""
+    from gnn_motion_planning_b200.algorithm import construct_graph
+    from gnn_motion_planning_b200.environment import MazeEnv
+    gold = np.load(os.path.join(G, "construct_graph.npz"))
+    mp = np.load(os.path.join(G, "maze_problems.npz"))
+    env = MazeEnv(dim=2, map_file=os.path.join(G, "maze_problems.npz"))
+    for pid in gold["ids"]:
+        tag = "p%d" % pid
+        env.init_new_problem(int(np.flatnonzero(mp["ids"] == pid)[0]))
+        pts = gold[tag + "_points"]
+        c0 = env.collision_check_count
+        edge_cost, neighbors, edge_index, edge_free = construct_graph(env, pts)
+        assert np.array_equal(edge_index, gold[tag + "_edge_index"]) and edge_index.dtype == np.int64
+        assert np.array_equal(np.array(edge_free), gold[tag + "_edge_free"])
+        assert env.collision_check_count - c0 == int(gold[tag + "_checks"])
+        assert np.array_equal(np.array([len(neighbors[i]) for i in range(len(pts))]), gold[tag + "_deg"])
+        assert np.array_equal(np.concatenate([np.asarray(neighbors[i], np.int64) for i in range(len(pts))]), gold[tag + "_nbr_flat"])
+        assert np.array_equal(np.concatenate([np.asarray(edge_cost[i], np.float64) for i in range(len(pts))]), gold[tag + "_cost_flat"])

@@ -159,3 +159,46 @@ def test_explore_with_model_smoother_golden(cuda_device):
         assert r["c_smooth"] == int(gold["p%d_c_smooth" % pid]), pid
         assert np.abs(np.array(r["smooth_path"]) - gold["p%d_smooth_path" % pid]).max() < 2e-4
         assert path_cost(r["smooth_path"]) <= path_cost(r["path"]) + 1e-6
+
+
+def test_steering_rounds_on_device_golden(cuda_device):
+    """gmp_maze_steer_rounds: all 30 steering calls of the reference run as ONE batch -- paths bit for bit,
+    collision_check_count exact, path cost as eval_gnn.path_cost gives it."""
+    from gnn_motion_planning_b200.eval_gnn import path_cost
+    from gnn_motion_planning_b200.smoother import steer_rounds_batch
+    gold = np.load(os.path.join(G, "model_smooth.npz"))
+    mp = np.load(os.path.join(G, "maze_problems.npz"))
+    olds, news, outs, checks, probs = [], [], [], [], []
+    for pid in gold["ids"]:
+        for j in range(int(gold["p%d_n_steer" % pid])):
+            olds.append(gold["p%d_steer%d_old" % (pid, j)]); news.append(gold["p%d_steer%d_new" % (pid, j)])
+            outs.append(gold["p%d_steer%d_out" % (pid, j)]); checks.append(int(gold["p%d_steer%d_checks" % (pid, j)]))
+            probs.append(int(np.flatnonzero(mp["ids"] == pid)[0]))
+    assert all(o.dtype == np.float32 for o in olds)
+    ptr = np.concatenate([[0], np.cumsum([len(o) for o in olds])]).astype(np.int32)
+    dev = cuda_device
+    out, chk, rounds, cost = steer_rounds_batch(torch.from_numpy(np.concatenate(olds)).to(dev), torch.from_numpy(np.concatenate(news)).to(dev),
+                                                torch.from_numpy(ptr).to(dev), torch.from_numpy(mp["maps"]).to(dev),
+                                                torch.tensor(probs, dtype=torch.int32, device=dev), 0.05, want_cost=True)
+    out, chk, cost = out.cpu().numpy(), chk.cpu().numpy(), cost.cpu().numpy()
+    for i, want in enumerate(outs):
+        assert np.array_equal(out[ptr[i]:ptr[i + 1]], want), i
+        assert chk[i] == checks[i], i
+        assert abs(cost[i] - path_cost(list(want))) < 1e-6
+    assert len(outs) == 30
+
+
+def test_model_smooth_batch_golden(cuda_device):
+    """model_smooth for all six problems in one batch, paths device-resident across the five iterations."""
+    from gnn_motion_planning_b200.smoother import model_smooth_batch
+    gold = np.load(os.path.join(G, "model_smooth.npz"))
+    mp = np.load(os.path.join(G, "maze_problems.npz"))
+    m = make("smooth_2d_attv3.pt", 2, cuda_device)
+    pids = [int(p) for p in gold["ids"]]
+    paths, checks, cost = model_smooth_batch(m, [gold["p%d_ms_free" % p] for p in pids], [gold["p%d_ms_collided" % p] for p in pids],
+                                             [gold["p%d_ms_path" % p] for p in pids], torch.from_numpy(mp["maps"]).to(cuda_device),
+                                             [int(np.flatnonzero(mp["ids"] == p)[0]) for p in pids])
+    for i, p in enumerate(pids):
+        want = gold["p%d_ms_out" % p]
+        assert np.abs(paths[i] - want).max() < 2e-4, (p, np.abs(paths[i] - want).max())
+        assert int(checks[i]) == int(gold["p%d_ms_checks" % p]), p

@@ -27,9 +27,10 @@ def construct_graph(env, points, check_collision=True, k=5):
     edge_index = ei.cpu().numpy().T.copy()
     a, b = points[edge_index[:, 0]], points[edge_index[:, 1]]
     free = env.edge_fp_batch(a, b)                                                      # env._edge_fp(points[e0], points[e1])  (:24)
-    cost = np.linalg.norm(b - a, axis=1)
     edge_cost, neighbors = defaultdict(list), defaultdict(list)
-    for (s, t), f, c in zip(edge_index, free, cost):
-        edge_cost[t].append(c if f else INFINITY)
+    for (s, t), f in zip(edge_index, free):
+        # (per-edge 1-D norm, as the reference: NumPy's vector norm goes through dot() and can differ from an axis-wise
+        #  sqrt(sum(d*d)) in the last bit)
+        edge_cost[t].append(np.linalg.norm(points[t] - points[s]) if f else INFINITY)
         neighbors[t].append(s)
     return edge_cost, neighbors, edge_index, [bool(f) for f in free]

@@ -42,6 +42,8 @@ SIGNATURES = {
                                      c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_int64, c_void_p]),
     "gmp_search_result_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p]),
+    "gmp_maze_sample_points": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, ctypes.c_uint64, c_void_p, c_void_p,
+                                       c_void_p, c_void_p, c_void_p]),
     "gmp_maze_steer_rounds": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, ctypes.c_double, c_void_p, c_void_p,
                                       c_void_p, c_void_p, c_void_p]),
     "gmp_arm_model_count": (c_int, []),

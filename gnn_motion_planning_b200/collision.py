@@ -89,6 +89,29 @@ def result_rows(logits, edge_free, edge_ptr_d, first_problem_id=0, out=None):
     return rows
 
 
+@torch.no_grad()
+def maze_sample_points(maps, problem_of_slot, stream_of_slot, n_points, seed, first_draw=None, cap_collided=None):
+    """Batched ``env.sample_n_points(n_points, need_negative=True)`` (maze_env.py:85-100) with the counter-based device RNG
+    (``gmp_maze_sample_points``): -> (free [S,n,2] f64, collided [S,cap,2] f64, n_collided [S] i32, n_draws [S] i64), all CUDA.
+    Slot s continues stream ``stream_of_slot[s]`` at draw ``first_draw[s]`` (0 if None)."""
+    _lib.require_cuda(maps, "maps")
+    lib = _lib.load()
+    dev = maps.device
+    prob = torch.as_tensor(problem_of_slot).to(device=dev, dtype=torch.int32).contiguous()
+    strm = torch.as_tensor(stream_of_slot).to(device=dev, dtype=torch.int64).contiguous()
+    fd = None if first_draw is None else torch.as_tensor(first_draw).to(device=dev, dtype=torch.int64).contiguous()
+    S = prob.numel()
+    cap = int(cap_collided if cap_collided is not None else 8 * n_points)
+    free = torch.empty((S, n_points, 2), dtype=torch.float64, device=dev)
+    coll = torch.empty((S, max(cap, 1), 2), dtype=torch.float64, device=dev)
+    n_coll = torch.empty(S, dtype=torch.int32, device=dev)
+    n_draws = torch.empty(S, dtype=torch.int64, device=dev)
+    _lib.check(lib.gmp_maze_sample_points(_lib.ptr(maps.to(torch.uint8).contiguous()), _lib.ptr(prob), _lib.ptr(strm), _lib.ptr(fd), S,
+                                          int(n_points), cap, int(seed) & 0xFFFFFFFFFFFFFFFF, _lib.ptr(free), _lib.ptr(coll),
+                                          _lib.ptr(n_coll), _lib.ptr(n_draws), _lib.stream_ptr(dev)))
+    return free, coll, n_coll, n_draws
+
+
 # ------------------------------------------------------------------------------------------------ arms
 ARM_KUKA7, ARM_KUKA14, ARM_KUKA13, ARM_UR5, ARM_SNAKE7 = 0, 1, 2, 3, 4
 

@@ -478,6 +478,77 @@ __global__ void __launch_bounds__(32) maze_steer_kernel(const float* __restrict_
   }
 }
 
+// =====================================================================================================================
+// Batched rejection sampler with a counter-based RNG                       (maze_env.py:85-100, 127-135)
+// =====================================================================================================================
+// The reference draws np.random.uniform(-1, 1, 2) one state at a time from the GLOBAL NumPy stream until n states are free;
+// rejected draws are kept as `collided`.  Its stream cannot be reproduced in parallel (every draw is coupled to the previous
+// check), so this sampler is a NEW stream with the same semantics: draw k of problem p is Philox4x32-10(key = seed,
+// counter = (k, stream id of p)) -> two doubles uniform in [-1, 1) (53-bit), and the result is the PREFIX of that fixed
+// sequence up to its n-th free draw -- independent of how many lanes evaluate it.  One warp per problem, 32 draws per step,
+// ballot + prefix popcount keep the draw order.  Parity with the reference is distributional (tests: free / collided
+// classification exact, prefix property, free fraction = free area of the map).
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* out) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__global__ void __launch_bounds__(32) maze_sample_kernel(const uint8_t* __restrict__ maps, const int32_t* __restrict__ problem_of_slot,
+                                                         const int64_t* __restrict__ stream_of_slot, const int64_t* __restrict__ first_draw,
+                                                         int n_slots, int n_want, int cap_collided, uint64_t seed, double* __restrict__ free_out,
+                                                         double* __restrict__ collided_out, int32_t* __restrict__ n_collided_out,
+                                                         int64_t* __restrict__ n_draws_out) {
+  const int sidx = blockIdx.x;
+  if (sidx >= n_slots) return;
+  const int lane = threadIdx.x;
+  const uint8_t* map = maps + (int64_t)problem_of_slot[sidx] * (kW * kW);
+  const uint64_t stream = (uint64_t)stream_of_slot[sidx];
+  uint64_t k = first_draw ? (uint64_t)first_draw[sidx] : 0;     // continue a stream across resampling rounds
+  const uint64_t k_begin = k;
+  double* fo = free_out + (size_t)sidx * n_want * 2;
+  double* co = collided_out + (size_t)sidx * cap_collided * 2;
+  int nf = 0, nc = 0;
+  while (nf < n_want) {
+    const uint64_t kk = k + lane;
+    uint32_t r[4];
+    philox4x32_10((uint32_t)kk, (uint32_t)(kk >> 32), (uint32_t)stream, (uint32_t)(stream >> 32), (uint32_t)seed, (uint32_t)(seed >> 32), r);
+    const double x = (double)((((uint64_t)r[0] << 32) | r[1]) >> 11) * (2.0 / 9007199254740992.0) - 1.0;
+    const double y = (double)((((uint64_t)r[2] << 32) | r[3]) >> 11) * (2.0 / 9007199254740992.0) - 1.0;
+    const bool ok = cell_free(map, x, y);                       // every draw is inside the limits: one counted lookup
+    const uint32_t fm = __ballot_sync(0xffffffffu, ok);
+    const int before_f = __popc(fm & ((1u << lane) - 1u));
+    // draws after the one that completes the n_want-th free state are not consumed
+    const int need = n_want - nf;
+    int last = 31;                                              // last consumed lane of this step
+    if (__popc(fm) >= need) {
+      uint32_t m = fm;
+      for (int i = 1; i < need; ++i) m &= m - 1;                // clear the first need-1 set bits
+      last = __ffs(m) - 1;
+    }
+    if (lane <= last) {
+      if (ok) { fo[2 * (nf + before_f)] = x; fo[2 * (nf + before_f) + 1] = y; }
+      else {
+        const int j = nc + (lane - before_f);
+        if (j < cap_collided) { co[2 * j] = x; co[2 * j + 1] = y; }
+      }
+    }
+    const uint32_t used = last == 31 ? 0xffffffffu : ((2u << last) - 1u);
+    nf += __popc(fm & used);
+    nc += __popc(~fm & used);
+    k += (uint64_t)(last + 1);
+  }
+  if (lane == 0) {
+    n_collided_out[sidx] = nc;
+    n_draws_out[sidx] = (int64_t)(k - k_begin);
+  }
+}
+
 // per-problem rows of the final reduction (eval_gnn.py:120-134): (problem id, success, path cost, collision checks of the search,
 // speculative checks never committed, explored nodes) -- the payload of the multi-GPU all-gather
 __global__ void search_rows_kernel(const int32_t* __restrict__ status, const float* __restrict__ path_cost, const int32_t* __restrict__ n_checks,
@@ -621,6 +692,19 @@ extern "C" int gmp_maze_steer_rounds(const float* old_path, const float* new_pat
   GMP_REQUIRE(old_path && new_path && path_ptr && maps && path_out && n_checks_out, "null pointer");
   maze_steer_kernel<<<(unsigned)((n_paths + 31) / 32), 32, 0, static_cast<cudaStream_t>(stream)>>>(
       old_path, new_path, path_ptr, maps, problem_of_path, (int)n_paths, (float)rrt_eps, path_out, n_checks_out, n_rounds_out, path_cost_out);
+  GMP_LAUNCH_CHECK();
+  return GMP_OK;
+}
+
+extern "C" int gmp_maze_sample_points(const uint8_t* maps, const int32_t* problem_of_slot, const int64_t* stream_of_slot,
+                                      const int64_t* first_draw, int64_t n_slots, int32_t n_points, int32_t cap_collided, uint64_t seed,
+                                      double* free_out, double* collided_out, int32_t* n_collided_out, int64_t* n_draws_out, void* stream) {
+  GMP_REQUIRE(n_slots >= 0 && n_points >= 1 && cap_collided >= 0, "bad size");
+  if (n_slots == 0) return GMP_OK;
+  GMP_REQUIRE(maps && problem_of_slot && stream_of_slot && free_out && collided_out && n_collided_out && n_draws_out, "null pointer");
+  maze_sample_kernel<<<(unsigned)n_slots, 32, 0, static_cast<cudaStream_t>(stream)>>>(maps, problem_of_slot, stream_of_slot, first_draw, (int)n_slots,
+                                                                                     n_points, cap_collided, seed, free_out, collided_out,
+                                                                                     n_collided_out, n_draws_out);
   GMP_LAUNCH_CHECK();
   return GMP_OK;
 }

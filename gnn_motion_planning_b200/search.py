@@ -113,10 +113,29 @@ def _sample_batch(rngs, need, maps_d, problem_ids, device):
 
 
 @torch.no_grad()
+def _sample_batch_device(seed, streams, next_draw, need, maps_d, problem_ids):
+    """The same contract through the counter-based device sampler (``gmp_maze_sample_points``): one launch for all problems, no
+    host RNG.  ``next_draw`` (per problem) is advanced by the draws consumed."""
+    n = need[0]
+    assert all(x == n for x in need)
+    free_d, coll_d, n_coll, n_draws = collision.maze_sample_points(maps_d, problem_ids, streams, n, seed, first_draw=next_draw,
+                                                                   cap_collided=16 * n)
+    free_h, coll_h, n_coll, n_draws = free_d.cpu().numpy(), coll_d.cpu().numpy(), n_coll.cpu().numpy(), n_draws.cpu().numpy()
+    free = [list(free_h[i]) for i in range(len(streams))]
+    coll = [list(coll_h[i, :min(int(n_coll[i]), coll_h.shape[1])]) for i in range(len(streams))]
+    for i in range(len(streams)):
+        next_draw[i] += int(n_draws[i])
+    return free, coll, n_draws.astype(np.int64)
+
+
+@torch.no_grad()
 def explore_batch(model, maps, init_states, goal_states, problem_ids, seeds, batch=100, t_max=100, k=10, loop=5, spec_k=1,
-                  device=None, max_checks=20000):
+                  device=None, max_checks=20000, sampler="numpy"):
     """``explore(env, model, None, smooth=True, batch, t_max, k, smoother='none')`` for every problem of ``problem_ids``
     (rows of ``maps`` / ``init_states`` / ``goal_states``), seeded like ``np.random.seed(seeds[i])`` before the reference call.
+
+    sampler: "numpy" -- every problem owns np.random.RandomState(seeds[i]): the reference's exact stream (parity tests);
+             "device" -- the counter-based Philox sampler on the GPU (seeds[i] = stream id; a new stream, same semantics).
 
     Returns one dict per problem: success, path (float32 waypoints), path_nodes, explored (node ids in tree order), c_explore
     (= env.collision_check_count delta: sampling + edge + goal-region checks), spec_checks (speculative edge checks that were
@@ -131,7 +150,11 @@ def explore_batch(model, maps, init_states, goal_states, problem_ids, seeds, bat
     cap_nodes = 2 * (t_max + 2 * n_batch + 2) + 8
     st = TreeSearchState(P, cap_nodes, 2 + 4 * max_checks, dev)
 
-    new_free, new_coll, counted = _sample_batch(rngs, [n_batch] * P, maps_d, problem_ids, dev)
+    next_draw = [0] * P
+    if sampler == "device":
+        new_free, new_coll, counted = _sample_batch_device(0x9E3779B97F4A7C15, list(seeds), next_draw, [n_batch] * P, maps_d, problem_ids)
+    else:
+        new_free, new_coll, counted = _sample_batch(rngs, [n_batch] * P, maps_d, problem_ids, dev)
     free = [[np.asarray(init_states[problem_ids[p]]), np.asarray(goal_states[problem_ids[p]])] + new_free[p] for p in range(P)]
     coll = [new_coll[p][:len(new_free[p])] for p in range(P)]                      # collided = collided[:len(free)] BEFORE init/goal join (:180-181)
     c_sample = counted.copy()
@@ -175,7 +198,14 @@ def explore_batch(model, maps, init_states, goal_states, problem_ids, seeds, bat
             if status[p] == STATUS_EXHAUSTED and (n_batch + len(free[p]) - 2) <= t_max:      # eval_gnn.py:239-240
                 nxt.append(p)
         if nxt:                                                                               # resample (:242-247)
-            nf, nc, cnt = _sample_batch([rngs[p] for p in nxt], [n_batch] * len(nxt), maps_d, [problem_ids[p] for p in nxt], dev)
+            if sampler == "device":
+                nd = [next_draw[p] for p in nxt]
+                nf, nc, cnt = _sample_batch_device(0x9E3779B97F4A7C15, [seeds[p] for p in nxt], nd, [n_batch] * len(nxt), maps_d,
+                                                   [problem_ids[p] for p in nxt])
+                for i, p in enumerate(nxt):
+                    next_draw[p] = nd[i]
+            else:
+                nf, nc, cnt = _sample_batch([rngs[p] for p in nxt], [n_batch] * len(nxt), maps_d, [problem_ids[p] for p in nxt], dev)
             for i, p in enumerate(nxt):
                 free[p] = free[p] + nf[i]
                 coll[p] = (coll[p] + nc[i])[:len(free[p])]

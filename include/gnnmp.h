@@ -169,6 +169,16 @@ int gmp_maze_tree_search(const float* v, const int32_t* node_ptr, const int32_t*
 int gmp_search_result_rows(const int32_t* status, const float* path_cost, const int32_t* n_checks, const int32_t* n_spec_checks,
                            const int32_t* n_explored, int64_t n_problems, int32_t first_problem_id, float* rows_out, void* stream);
 
+/* Batched env.sample_n_points(n, need_negative=True) (maze_env.py:85-100) with a counter-based RNG: slot s draws the fixed
+ * sequence Philox4x32-10(key = seed, counter = (k, stream_of_slot[s])), k = first_draw[s], first_draw[s]+1, ... -> states
+ * uniform in [-1,1)^2 (float64), and returns the prefix of that sequence up to its n_points-th free state: free_out
+ * [S, n_points, 2], collided_out [S, cap_collided, 2] (the rejected draws, in draw order; n_collided_out may exceed
+ * cap_collided, then the tail is dropped), n_draws_out [S] = draws consumed = collision_check_count increments.  A NEW stream:
+ * parity with the reference's global NumPy stream is distributional only (the host mirror keeps the exact stream). */
+int gmp_maze_sample_points(const uint8_t* maps, const int32_t* problem_of_slot, const int64_t* stream_of_slot,
+                           const int64_t* first_draw, int64_t n_slots, int32_t n_points, int32_t cap_collided, uint64_t seed,
+                           double* free_out, double* collided_out, int32_t* n_collided_out, int64_t* n_draws_out, void* stream);
+
 /* Replaces proposed_path_smootherv2 (smoother.py:194-216) for a packed batch of 2-D maze paths: K = ceil(max ||old - new|| /
  * rrt_eps) rounds; per round every interior waypoint is steered at most rrt_eps toward its proposal and kept iff both adjacent
  * edges are collision free (against the already updated left neighbour); stops when the accepted waypoints have all reached

@@ -88,3 +88,53 @@ def test_batch_equals_host_loop(cuda_device, setup):
         assert r["success"] == h["success"] and r["explored"] == h["explored"] and r["c_explore"] == h["c_explore"], row
         if h["success"]:
             assert np.allclose(np.array(r["path"]), np.array(h["path"]))
+
+
+def test_device_sampler_semantics(cuda_device, setup):
+    """gmp_maze_sample_points: a counter-based stream with the reference's rejection-sampling semantics --
+    every returned free state is free and every rejected one is not (bit-exact state checks), draws = free + rejected, the
+    result is a PREFIX of one fixed sequence (sampling 40 then 60 more == sampling 100), streams differ, and the accepted
+    fraction matches the free area of the map."""
+    from gnn_motion_planning_b200 import collision
+    mp, _ = setup
+    dev = cuda_device
+    maps_d = torch.from_numpy(mp["maps"]).to(dev)
+    probs = [0, 3, 6, 6]
+    streams = [11, 12, 13, 14]
+    free, coll, n_coll, n_draws = collision.maze_sample_points(maps_d, probs, streams, 100, seed=7)
+    free_h, coll_h, n_coll, n_draws = free.cpu().numpy(), coll.cpu().numpy(), n_coll.cpu().numpy(), n_draws.cpu().numpy()
+    assert free_h.dtype == np.float64 and np.all(np.abs(free_h) <= 1.0)
+    for i, p in enumerate(probs):
+        assert n_draws[i] == 100 + n_coll[i]
+        pr = torch.full((100,), p, dtype=torch.int32, device=dev)
+        assert bool(collision.maze_state_fp(free[i], maps_d, pr).all())
+        nc = int(n_coll[i])
+        prc = torch.full((nc,), p, dtype=torch.int32, device=dev)
+        assert not bool(collision.maze_state_fp(coll[i, :nc].contiguous(), maps_d, prc).any())
+        area = float((mp["maps"][p] == 0).mean())
+        assert abs(100.0 / n_draws[i] - area) < 0.15                                   # accepted fraction ~ free area
+    assert not np.array_equal(free_h[2], free_h[3])                                   # same map, different streams
+    # prefix property + continuation (first_draw)
+    f40, _, c40, d40 = collision.maze_sample_points(maps_d, probs, streams, 40, seed=7)
+    assert np.array_equal(f40.cpu().numpy(), free_h[:, :40])
+    f60, _, c60, d60 = collision.maze_sample_points(maps_d, probs, streams, 60, seed=7, first_draw=d40)
+    assert np.array_equal(f60.cpu().numpy(), free_h[:, 40:])
+    assert np.array_equal((d40 + d60).cpu().numpy(), n_draws)
+
+
+def test_explore_batch_with_device_sampler(cuda_device, setup):
+    """The whole planner round on the device sampler: different samples than the NumPy stream, same planner quality band."""
+    from gnn_motion_planning_b200.search import explore_batch
+    mp, model = setup
+    rows = list(range(len(mp["ids"])))
+    a = explore_batch(model, mp["maps"], mp["init_states"], mp["goal_states"], rows, [500 + r for r in rows], batch=100, t_max=300, k=10,
+                      device=cuda_device, sampler="device")
+    b = explore_batch(model, mp["maps"], mp["init_states"], mp["goal_states"], rows, [500 + r for r in rows], batch=100, t_max=300, k=10,
+                      device=cuda_device, sampler="device")
+    assert [r["explored"] for r in a] == [r["explored"] for r in b]                    # deterministic
+    n = explore_batch(model, mp["maps"], mp["init_states"], mp["goal_states"], rows, [500 + r for r in rows], batch=100, t_max=300, k=10,
+                      device=cuda_device)
+    assert sum(r["success"] for r in a) >= sum(r["success"] for r in n) - 2
+    for r in a:
+        if r["success"]:
+            assert r["path_nodes"][0] == 0 and r["c_explore"] > 0

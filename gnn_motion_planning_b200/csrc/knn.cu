@@ -24,6 +24,8 @@
 //
 // Bound: integer/bit work out of L1/L2 (a graph's v is <= 112 KB); HBM traffic is the output
 // (16 B per edge, int64 pairs) plus N*c*4 B in.  See DESIGN.md.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace gmp {
@@ -182,6 +184,123 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, NPL <= 16 ? 5 : (NPL <= 32 
 #pragma unroll
       for (int t = 0; t < NPL; ++t) cl += (d[t] < T) ? 1 : 0;
       n_less = __reduce_add_sync(0xffffffffu, cl);
+    }
+    int quota = k - min(n_less, k);
+#pragma unroll
+    for (int t = 0; t < NPL; ++t) {
+      const int j = lane + 32 * t;
+      const bool in = j < cnt;
+      const bool less = in && d[t] < T;
+      const bool tie = in && (d[t] == T) && (k < cnt);
+      const uint32_t tb = __ballot_sync(0xffffffffu, tie);
+      const bool take = less || (tie && __popc(tb & ((1u << lane) - 1u)) < quota);
+      quota -= min(quota, __popc(tb));
+      if (take) {
+        atomicOr(bm + (size_t)i * wpr + (j >> 5), 1u << (j & 31));
+        atomicOr(bm + (size_t)j * wpr + (i >> 5), 1u << (i & 31));
+      }
+    }
+  }
+}
+
+// Round-2 select kernel (graphs of at most 32*NPL nodes whose transposed node block fits in shared memory):
+//  * one CTA serves a CHUNK of centres of one graph; the graph's candidate block is staged once in shared memory, TRANSPOSED
+//    (vT[q][j], odd pitch): the distance loop reads lane-contiguous, conflict-free words instead of c-strided global words
+//    (c = 14: 56-byte stride, 14 sectors per warp load in the register-strip kernel above);
+//  * the k-th smallest distance is found in TWO levels instead of 31 bisection passes over every candidate: 12 passes fix the
+//    top bits (sign-less exponent + 4 mantissa bits); the candidates that share those bits with the threshold -- a handful --
+//    are compacted into one register per lane (ballot + find-n-th-set + shuffle) and the remaining 19 bits are bisected on that
+//    single register.  Same threshold, same tie rule (distance, then index): the edge set is bit-identical.
+template <int NPL>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, NPL <= 32 ? 4 : 2) knn_select_smem_kernel(
+    const float* __restrict__ v, int c, const int32_t* __restrict__ node_ptr, const int32_t* __restrict__ n_free,
+    const int32_t* __restrict__ k1s, const int64_t* __restrict__ bm_ptr, int centres_per_cta, uint32_t* __restrict__ bitmap) {
+  extern __shared__ float vT[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = blockIdx.y, pass = blockIdx.z;
+  const int n0 = node_ptr[g], n = node_ptr[g + 1] - n0, nf = n_free[g];
+  if (pass == 1 && nf >= n) return;                        // the free-only graph is the whole graph
+  const int cnt = pass == 0 ? n : nf;                      // candidates = centres of this pass
+  const int i_lo = blockIdx.x * centres_per_cta, i_hi = min(i_lo + centres_per_cta, cnt);
+  if (i_lo >= i_hi) return;
+  const int pitch = (cnt + 1) | 1;
+  const float* vg = v + (size_t)n0 * c;
+  for (int idx = threadIdx.x; idx < cnt * c; idx += kWarpsPerCta * 32) {
+    const int j = idx / c, q = idx - j * c;
+    vT[q * pitch + j] = __ldg(vg + idx);
+  }
+  __syncthreads();
+  const int k = min(k1s[g], cnt);
+  const int wpr = (n + 31) >> 5;
+  uint32_t* bm = bitmap + bm_ptr[g];
+  constexpr int L = 19;                                    // bits resolved on the compacted bucket
+  for (int i = i_lo + warp; i < i_hi; i += kWarpsPerCta) {
+    uint32_t d[NPL];
+#pragma unroll
+    for (int t = 0; t < NPL; ++t) d[t] = 0xffffffffu;      // padding: never below any threshold
+    for (int q = 0; q < c; ++q) {
+      const float xi = vT[q * pitch + i];
+      const float* col = vT + q * pitch + lane;
+#pragma unroll
+      for (int t = 0; t < NPL; ++t) {
+        if (lane + 32 * t < cnt) {
+          const float diff = __fsub_rn(xi, col[32 * t]);
+          const float prev = q == 0 ? 0.0f : __uint_as_float(d[t]);
+          d[t] = __float_as_uint(__fadd_rn(prev, __fmul_rn(diff, diff)));
+        }
+      }
+    }
+    uint32_t T = 0xffffffffu;
+    int n_less = cnt;
+    if (k < cnt) {
+      T = 0;
+      auto count_below = [&](uint32_t cand) {
+        int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+#pragma unroll
+        for (int t = 0; t < NPL; t += 4) {
+          c0 += (d[t] < cand) ? 1 : 0; c1 += (d[t + 1] < cand) ? 1 : 0; c2 += (d[t + 2] < cand) ? 1 : 0; c3 += (d[t + 3] < cand) ? 1 : 0;
+        }
+        return __reduce_add_sync(0xffffffffu, (c0 + c1) + (c2 + c3));
+      };
+      int n_below = 0;                                     // count(d < T) for the current T
+#pragma unroll 1
+      for (int bit = 30; bit >= L; --bit) {
+        const uint32_t cand = T | (1u << bit);
+        const int cl = count_below(cand);
+        if (cl < k) { T = cand; n_below = cl; }
+      }
+      // bucket: candidates with the threshold's top bits -> one register per lane
+      uint32_t e = 0xffffffffu;
+      int nb = 0;
+#pragma unroll
+      for (int t = 0; t < NPL; ++t) {
+        const bool inb = (d[t] >> L) == (T >> L);
+        const uint32_t b = __ballot_sync(0xffffffffu, inb);
+        if (b) {
+          const int want = lane - nb;                      // this lane takes the want-th bucket member of this step
+          const int pc = __popc(b);
+          const uint32_t src = (want >= 0 && want < pc) ? __fns(b, 0, want + 1) : 0u;
+          const uint32_t val = __shfl_sync(0xffffffffu, d[t], src & 31);
+          if (want >= 0 && want < pc) e = val;
+          nb += pc;
+        }
+      }
+      if (nb <= 32) {
+#pragma unroll 1
+        for (int bit = L - 1; bit >= 0; --bit) {
+          const uint32_t cand = T | (1u << bit);
+          const int cl = n_below + __popc(__ballot_sync(0xffffffffu, e < cand));
+          if (cl < k) T = cand;
+        }
+        n_less = n_below + __popc(__ballot_sync(0xffffffffu, e < T));
+      } else {                                             // (many near-equal distances: finish on the full strip)
+#pragma unroll 1
+        for (int bit = L - 1; bit >= 0; --bit) {
+          const uint32_t cand = T | (1u << bit);
+          if (count_below(cand) < k) T = cand;
+        }
+        n_less = count_below(T);
+      }
     }
     int quota = k - min(n_less, k);
 #pragma unroll
@@ -404,6 +523,24 @@ extern "C" int gmp_knn_graph(gmp_handle* /*h*/, int64_t n_graphs, const float* v
     GMP_CUDA(cudaFuncSetAttribute(knn_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int gx = (int)((n_total + kWarpsPerCta - 1) / kWarpsPerCta);
     if (gx > kNumSMs * 16) gx = kNumSMs * 16;
+    // round-2 kernel: transposed node block in shared memory + two-level threshold search (per-graph grid)
+    const size_t smem_t = (size_t)c * (size_t)((max_n + 1) | 1) * sizeof(float);
+    const bool use_smem = max_n <= 2048 && smem_t <= 113 * 1024 && n_graphs <= 65535 && !getenv("GMP_KNN_LEGACY");
+    if (use_smem) {
+      // ~16 centres per warp: enough to amortise the staging of the node block, enough CTAs to fill the device
+      const int cpc = 128;
+      const dim3 grid((unsigned)((max_n + cpc - 1) / cpc), (unsigned)n_graphs, 2);
+#define GMP_KNN_SMEM(NPL_)                                                                                                      \
+      {                                                                                                                         \
+        GMP_CUDA(cudaFuncSetAttribute(knn_select_smem_kernel<NPL_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t)); \
+        knn_select_smem_kernel<NPL_><<<grid, kWarpsPerCta * 32, smem_t, st>>>(v, c, ws.node_ptr, ws.n_free, ws.k1, ws.bm_ptr, cpc, ws.bitmap); \
+      }
+      if (max_n <= 256) GMP_KNN_SMEM(8)
+      else if (max_n <= 512) GMP_KNN_SMEM(16)
+      else if (max_n <= 1024) GMP_KNN_SMEM(32)
+      else GMP_KNN_SMEM(64)
+#undef GMP_KNN_SMEM
+    } else
     if (max_n <= 256)
       knn_select_reg_kernel<8><<<dim3(gx, 2), kWarpsPerCta * 32, 0, st>>>(v, c, ws.node_ptr, ws.n_free, ws.k1, ws.bm_ptr, (int)n_graphs,
                                                                           (int)n_total, ws.bitmap);

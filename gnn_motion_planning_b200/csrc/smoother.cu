@@ -59,7 +59,9 @@ __global__ void __launch_bounds__(256) smoother_graph_kernel(
     const float* __restrict__ nodes, int c, const int32_t* __restrict__ nd_ptr, const int32_t* __restrict__ path_len,
     const int64_t* __restrict__ edge_index, int64_t row_stride, const int32_t* __restrict__ edge_ptr,
     const int32_t* __restrict__ msg_ptr, const int32_t* __restrict__ prow_ptr, int strip, int32_t* __restrict__ msg_src,
-    int32_t* __restrict__ msg_dst, int32_t* __restrict__ seg_ptr /* [P_total + B] (P_g + 1 per problem) */) {
+    int32_t* __restrict__ msg_dst, int32_t* __restrict__ seg_ptr /* [P_total + B] (P_g + 1 per problem) */,
+    int32_t* __restrict__ act_node /* [N_total]: per problem, the nodes that are a path node or the source of a message */,
+    int32_t* __restrict__ act_cnt /* [B] */) {
   extern __shared__ __align__(16) unsigned char smem_u8[];
   const int g = blockIdx.x;
   const int n0 = nd_ptr[g], n = nd_ptr[g + 1] - n0;
@@ -138,6 +140,34 @@ __global__ void __launch_bounds__(256) smoother_graph_kernel(
     cnt[P] = run;
   }
   __syncthreads();
+  // ACTIVE nodes: x / A are read for message SOURCES only and h for path rows only (model_smoother.py:125-126,139), so the node
+  // MLP (three 128x128 products per row) runs on path nodes + the union of the rows' source sets -- at most P + 10 P + caller
+  // sources of ~1 000 nodes per problem.  Ascending node order: the path nodes come first.
+  if (threadIdx.x < 32) {
+    int base = 0;
+    for (int wb = 0; wb < wpr; wb += 32) {
+      const int w = wb + lane;
+      uint32_t bits = 0u;
+      if (w < wpr) {
+        for (int i = 0; i < P; ++i) bits |= bm[(size_t)i * wpr + w];
+        const int lo = w << 5;                       // path nodes [0, P) are always active
+        if (lo + 32 <= P) bits = 0xffffffffu;
+        else if (lo < P) bits |= (1u << (P - lo)) - 1u;
+        if (lo + 32 > n) bits &= (n - lo >= 32) ? 0xffffffffu : ((1u << (n - lo)) - 1u);
+      }
+      const int pc = __popc(bits);
+      int incl = pc;
+      for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+      int p = n0 + base + incl - pc;
+      while (bits) {
+        const int b = __ffs(bits) - 1;
+        bits &= bits - 1;
+        act_node[p++] = n0 + (w << 5) + b;
+      }
+      base += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) act_cnt[g] = base;
+  }
   const int m0 = msg_ptr[g];
   int32_t* seg = seg_ptr + prow_ptr[g] + g;
   for (int i = threadIdx.x; i <= P; i += 256) seg[i] = m0 + cnt[i];
@@ -163,22 +193,26 @@ template <int C>
 __global__ void __launch_bounds__(kRtThreads) smoother_node_kernel(SmootherW w, const float* __restrict__ W,
                                                                    const float* __restrict__ nodes, const int32_t* __restrict__ nd_ptr,
                                                                    const int32_t* __restrict__ path_len, const int32_t* __restrict__ free_len,
-                                                                   int n_graphs, int n_rows, float* __restrict__ Xg,
-                                                                   float* __restrict__ A, float* __restrict__ B) {
+                                                                   const int32_t* __restrict__ act_node, const int32_t* __restrict__ act_cnt,
+                                                                   float* __restrict__ Xg, float* __restrict__ A, float* __restrict__ B) {
   using Cf = RowCfg<kE>;
   constexpr int TM = Cf::TM, R = Cf::R, RP = Cf::RP;
   static_assert(TM == 1, "smoother tiles use one row per thread");
   extern __shared__ __align__(16) float smem_raw[];
   SmSmem sm(smem_raw);
   float* xcol = sm.X + threadIdx.x;
-  const int row = blockIdx.x * R + threadIdx.x;
-  const bool valid = row < n_rows;
+  // tile blockIdx.x of the ACTIVE nodes of problem blockIdx.y (smoother_graph_kernel); results land at the node's own row
+  const int g = blockIdx.y;
+  const int n_act = act_cnt[g];
+  if (blockIdx.x * R >= n_act) return;
+  const int arow = blockIdx.x * R + threadIdx.x;
+  const bool valid = arow < n_act;
+  const int row = valid ? act_node[nd_ptr[g] + arow] : 0;
   float in[1][C + 3];
 #pragma unroll
   for (int k = 0; k < C + 3; ++k) in[0][k] = 0.0f;
   bool is_path = false;
   if (valid) {
-    const int g = find_segment(nd_ptr, n_graphs, row);
     const int local = row - nd_ptr[g];
     is_path = local < path_len[g];
 #pragma unroll
@@ -339,7 +373,7 @@ __global__ void __launch_bounds__(256) smoother_pack_kernel(const float* __restr
 }
 
 struct SmWs {
-  int32_t *nd_ptr, *prow_ptr, *srow_ptr, *path_len, *free_len, *edge_ptr, *msg_ptr, *msg_src, *msg_dst, *seg_ptr;
+  int32_t *nd_ptr, *prow_ptr, *srow_ptr, *path_len, *free_len, *edge_ptr, *msg_ptr, *msg_src, *msg_dst, *seg_ptr, *act_node, *act_cnt;
   float *nodes, *Xg, *A, *B, *M;
 };
 
@@ -354,6 +388,8 @@ int64_t carve_smoother(Carver& cv, SmWs& ws, int c, int64_t B, int64_t Nt, int64
   ws.msg_src = cv.take<int32_t>(Mcap);
   ws.msg_dst = cv.take<int32_t>(Mcap);
   ws.seg_ptr = cv.take<int32_t>(Pt + B + 1);
+  ws.act_node = cv.take<int32_t>(Nt);
+  ws.act_cnt = cv.take<int32_t>(B);
   ws.nodes = cv.take<float>(Nt * c);
   ws.Xg = cv.take<float>(Nt * kE);
   ws.A = cv.take<float>(Nt * kE);
@@ -375,7 +411,7 @@ int run_smoother(gmp_handle* h, int64_t B, const float* path, const float* sampl
   int32_t* pl = mp + (B + 1);
   int32_t* fl = pl + B;
   nd[0] = mp[0] = 0;
-  int max_p = 0, max_s = 0;
+  int max_p = 0, max_s = 0, max_act = 1;
   for (int64_t g = 0; g < B; ++g) {
     const int P = path_ptr_h[g + 1] - path_ptr_h[g], S = sample_ptr_h[g + 1] - sample_ptr_h[g];
     const int ne = edge_ptr_h[g + 1] - edge_ptr_h[g];
@@ -387,8 +423,10 @@ int run_smoother(gmp_handle* h, int64_t B, const float* path, const float* sampl
     fl[g] = n_free_h[g];
     max_p = std::max(max_p, P);
     max_s = std::max(max_s, S);
+    max_act = std::max(max_act, std::min(P + S, P + kKnn * P + ne));   // path nodes + at most one new source per message
   }
   const int64_t Mcap = mp[B];
+  GMP_REQUIRE(B <= 65535, "more than 65535 problems per call (grid.y limit)");
   Carver cv(workspace);
   SmWs ws;
   GMP_REQUIRE(carve_smoother(cv, ws, C, B, Nt, Pt, Mcap) <= workspace_bytes, "workspace too small (see gmp_smoother_workspace_bytes)");
@@ -420,11 +458,12 @@ int run_smoother(gmp_handle* h, int64_t B, const float* path, const float* sampl
   for (int it = 0; it < loop; ++it) {
     if (Mcap > 0) GMP_CUDA(cudaMemsetAsync(ws.msg_src, 0xff, Mcap * sizeof(int32_t), st));
     smoother_graph_kernel<<<(int)B, 256, gsmem, st>>>(ws.nodes, C, ws.nd_ptr, ws.path_len, edge_index, row_stride, ws.edge_ptr,
-                                                      ws.msg_ptr, ws.prow_ptr, strip, ws.msg_src, ws.msg_dst, ws.seg_ptr);
+                                                      ws.msg_ptr, ws.prow_ptr, strip, ws.msg_src, ws.msg_dst, ws.seg_ptr, ws.act_node,
+                                                      ws.act_cnt);
     GMP_LAUNCH_CHECK();
     if (Nt > 0) {
-      smoother_node_kernel<C><<<(int)((Nt + R - 1) / R), kRtThreads, smem, st>>>(m.w, W, ws.nodes, ws.nd_ptr, ws.path_len, ws.free_len,
-                                                                                 (int)B, (int)Nt, ws.Xg, ws.A, ws.B);
+      smoother_node_kernel<C><<<dim3((unsigned)((max_act + R - 1) / R), (unsigned)B), kRtThreads, smem, st>>>(
+          m.w, W, ws.nodes, ws.nd_ptr, ws.path_len, ws.free_len, ws.act_node, ws.act_cnt, ws.Xg, ws.A, ws.B);
       GMP_LAUNCH_CHECK();
     }
     if (Mcap > 0) {

@@ -27,6 +27,7 @@ SIGNATURES = {
     "gmp_explorer_workspace_bytes": (c_int64, [c_void_p, c_int64, c_int64, c_int64, c_int64]),
     "gmp_explorer_forward": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "gmp_explorer_bad_edges": (c_int, [c_void_p, c_void_p]),
     "gmp_set_timing": (c_int, [c_void_p, c_int]),
     "gmp_get_timings": (c_int, [c_void_p, c_void_p, c_int]),
     "gmp_knn_graph_max_edges": (c_int64, [c_int64, c_int]),

@@ -32,6 +32,8 @@ class HotPath:
         self.node_ptr_d = torch.from_numpy(self.node_ptr).to(self.dev)
         self.n_free = np.full(self.B, self.N, np.int32)
         self.k1 = np.full(self.B, self.k, np.int32)
+        if maps is not None and maps.dtype != torch.uint8:      # reference map files are float64 {0,1}
+            maps = (maps != 0).to(torch.uint8).contiguous()
         self.maps, self.boxes, self.box_ptr, self.arm_model, self.rrt_eps = maps, boxes, box_ptr, arm_model, rrt_eps
         self.cap = int(self.B * _lib.load().gmp_knn_graph_max_edges(self.N, self.k))
         self.id_dtype = torch.int16 if self.N <= 32767 else torch.int32

@@ -67,6 +67,9 @@ def maze_edge_fp_graph(v, edge_index, node_ptr_d, edge_ptr_d, maps, n_edges_tota
     """
     lib = _lib.load()
     _lib.handle(_dev_index(v))
+    if maps.dtype != torch.uint8 or not maps.is_contiguous():
+        raise TypeError("maps must be a contiguous uint8 tensor [P,15,15] (the reference's maze_files maps are float64: convert "
+                        "once with (maps != 0).to(torch.uint8))")
     B = node_ptr_d.numel() - 1
     free = free_out if free_out is not None else torch.empty(n_edges_total, dtype=torch.uint8, device=v.device)
     checks = checks_out

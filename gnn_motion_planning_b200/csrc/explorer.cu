@@ -192,10 +192,15 @@ __device__ __forceinline__ void encoder_mlp(const SM& sm, const float* __restric
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) csr_count_kernel(const int64_t* __restrict__ edge_index, int64_t row_stride,
                                                         const int32_t* __restrict__ edge_ptr, const int32_t* __restrict__ node_ptr,
-                                                        int n_graphs, int n_edges, int32_t* __restrict__ indeg) {
+                                                        int n_graphs, int n_edges, int32_t* __restrict__ indeg, int32_t* __restrict__ bad) {
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_edges; e += gridDim.x * blockDim.x) {
     const int g = find_segment(edge_ptr, n_graphs, e);
-    const int dst = (int)edge_index[row_stride + e];
+    const int n = node_ptr[g + 1] - node_ptr[g];
+    const int64_t s64 = edge_index[e], d64 = edge_index[row_stride + e];
+    // local ids outside [0, N_g) would write outside the workspace: they are clamped (memory safe, result undefined for that
+    // edge) and counted -- gmp_explorer_bad_edges() reports the count of the last forward
+    if (s64 < 0 || s64 >= n || d64 < 0 || d64 >= n) atomicAdd(bad, 1);
+    const int dst = (int)min(max(d64, (int64_t)0), (int64_t)max(n - 1, 0));
     atomicAdd(indeg + node_ptr[g] + dst, 1);
   }
 }
@@ -241,9 +246,9 @@ __global__ void __launch_bounds__(256) csr_fill_kernel(const int64_t* __restrict
                                                        int32_t* __restrict__ csr_dst, int32_t* __restrict__ csr_eid) {
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_edges; e += gridDim.x * blockDim.x) {
     const int g = find_segment(edge_ptr, n_graphs, e);
-    const int n0 = node_ptr[g];
-    const int src = n0 + (int)edge_index[e];
-    const int dst = n0 + (int)edge_index[row_stride + e];
+    const int n0 = node_ptr[g], nm1 = max(node_ptr[g + 1] - n0 - 1, 0);
+    const int src = n0 + (int)min(max(edge_index[e], (int64_t)0), (int64_t)nm1);                  // (clamped: see csr_count_kernel)
+    const int dst = n0 + (int)min(max(edge_index[row_stride + e], (int64_t)0), (int64_t)nm1);
     const int slot = in_ptr[dst] + atomicAdd(cursor + dst, 1);
     csr_src[slot] = src;
     csr_dst[slot] = dst;
@@ -1403,7 +1408,8 @@ int run_forward(gmp_handle* h, int64_t B, const float* v, const int64_t* edge_in
   if (Nt > 0) GMP_CUDA(cudaMemsetAsync(ws.indeg, 0, (Nt + 1) * sizeof(int32_t), st));
   if (Et > 0) {
     int gx = (int)std::min<int64_t>((Et + 255) / 256, kNumSMs * 16);
-    csr_count_kernel<<<gx, 256, 0, st>>>(edge_index, row_stride, ws.edge_ptr, ws.node_ptr, (int)B, (int)Et, ws.indeg);
+    csr_count_kernel<<<gx, 256, 0, st>>>(edge_index, row_stride, ws.edge_ptr, ws.node_ptr, (int)B, (int)Et, ws.indeg, ws.indeg + Nt);
+    h->ex_bad_edges = ws.indeg + Nt;
     GMP_LAUNCH_CHECK();
   }
   csr_scan_kernel<<<(int)B, 256, 0, st>>>(ws.indeg, ws.node_ptr, ws.edge_ptr, ws.in_ptr, ws.cursor);
@@ -1587,6 +1593,16 @@ extern "C" int gmp_explorer_set_tensor(gmp_handle* h, const char* name, const fl
   h->ex.tensors[name] = std::vector<float>(data_h, data_h + numel);
   h->ex.ready = false;
   return GMP_OK;
+}
+
+extern "C" int gmp_explorer_bad_edges(gmp_handle* h, void* stream) {
+  GMP_REQUIRE(h, "null handle");
+  if (!h->ex_bad_edges) return 0;
+  int32_t n = 0;
+  GMP_CUDA(cudaSetDevice(h->device));
+  GMP_CUDA(cudaMemcpyAsync(&n, h->ex_bad_edges, sizeof(n), cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)));
+  GMP_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+  return n;
 }
 
 extern "C" int gmp_explorer_set_edge_feature_mode(gmp_handle* h, int mode) {

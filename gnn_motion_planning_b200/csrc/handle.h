@@ -115,4 +115,5 @@ struct gmp_handle {
   // launch state of the explorer kernels on THIS handle's device (shared-memory opt-in done, persistent grid size)
   bool ex_attr_done = false;
   int ex_msg_grid = 0;
+  const int32_t* ex_bad_edges = nullptr;   // device counter (in the caller's workspace) of out-of-range edge ids in the last forward
 };

@@ -198,6 +198,14 @@ class EncoderProcessDecoder:
         code = {"auto": -1, "simt": 0, "tc": 1, "tc4": 2}[mode]
         _lib.check(_lib.load().gmp_explorer_set_edge_feature_mode(self._handle, code))
 
+    def last_bad_edges(self):
+        """Number of edge_index entries outside [0, N_g) in the last ``forward_batch`` / ``forward_sparse`` (they are clamped on
+        the device so that nothing is written out of bounds; the drop-in ``forward`` raises IndexError up front).  Synchronises."""
+        rc = _lib.load().gmp_explorer_bad_edges(self._handle, _lib.stream_ptr(self._device))
+        if rc < 0:
+            _lib.check(rc)
+        return rc
+
     def set_timing(self, enable=True):
         """Record CUDA events around every phase of subsequent forwards (see ``last_timings``)."""
         self._ensure_uploaded()

@@ -90,6 +90,11 @@ int gmp_explorer_forward(gmp_handle* h, int64_t n_graphs, const float* v, const 
                          float* edge_logits_out, float* dense_out, void* workspace, int64_t workspace_bytes,
                          void* stream);
 
+/* edge_index ids outside [0, N_g) cannot be rejected without a device round trip: gmp_explorer_forward CLAMPS them (memory
+ * safe; the logits of such edges are meaningless) and counts them.  This call synchronises `stream` and returns the count of
+ * the last forward on this handle (0 = every id was in range; the caller's workspace must still be alive). */
+int gmp_explorer_bad_edges(gmp_handle* h, void* stream);
+
 /* Optional device-side timing of the last gmp_explorer_forward on this handle (replaces the reference's
  * wall-clock Timer spans, environment/timer.py:6-25).  gmp_get_timings synchronises on the recorded events and
  * writes milliseconds per phase into ms_out_h[0..7]:

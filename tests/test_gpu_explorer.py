@@ -118,6 +118,12 @@ def test_errors(cuda_device):
         m(goal=v[0], loop=1, v=v, obstacles=torch.zeros(3, 2, device=cuda_device), edge_index=ei)
     with pytest.raises(_lib.GnnmpError):
         m.forward_batch(torch.zeros(10, 2), ei.cpu(), v[:1], None, [0, 10], [0, 2], [0, 0])
+    # the batched entry point cannot raise without a device round trip: bad ids are clamped (memory safe) and counted
+    out = m.forward_batch(v, ei, v[:1].contiguous(), torch.zeros(3, 2, device=cuda_device), [0, 10], [0, 2], [0, 3])
+    assert torch.isfinite(out).all() and m.last_bad_edges() == 1
+    good = torch.tensor([[0, 1], [1, 2]], device=cuda_device)
+    m.forward_batch(v, good, v[:1].contiguous(), torch.zeros(3, 2, device=cuda_device), [0, 10], [0, 2], [0, 3])
+    assert m.last_bad_edges() == 0
     # empty edge set / single node
     out = m(goal=v[0], loop=2, v=v[:1], obstacles=torch.zeros(0, 2, device=cuda_device),
             edge_index=torch.zeros(2, 0, dtype=torch.int64, device=cuda_device))

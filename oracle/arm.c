@@ -212,16 +212,18 @@ static int point_free(const ArmModel* m, const double* q, const double* boxes, i
       if (!state_valid(&m, qs) || !state_valid(&m, qt)) ok = 0;                           /* kuka_env.py:394 */      \
       else if (!point_free(&m, qs, bx, nb, &cnt) || !point_free(&m, qt, bx, nb, &cnt)) ok = 0; /* :397 */             \
       else {                                                                                                         \
-        /* d = sqrt(sum(|b - a|^2)) in T with numpy's summation order (8-way unrolled pairwise for n >= 8) */       \
-        T sq[GMP_ARM_MAX_JOINTS], d2;                                                                                \
-        for (int j = 0; j < dof; ++j) { T df = t[j] - s[j]; df = df < 0 ? -df : df; sq[j] = df * df; }               \
+        /* d = KukaEnv.distance (kuka_env.py:224-233): to_state is first clamped against the FLOAT64 pose_range, which promotes   */ \
+        /* the whole expression to float64 whatever the input dtype (a no-op in value: both states are within the limits);    */ \
+        /* numpy's summation order (8-way unrolled pairwise for n >= 8); K = int(d / RRT_EPS) in float64          (:403)      */ \
+        double sq[GMP_ARM_MAX_JOINTS], d2;                                                                           \
+        for (int j = 0; j < dof; ++j) { double df = (double)t[j] - (double)s[j]; df = df < 0 ? -df : df; sq[j] = df * df; } \
         if (dof < 8) { d2 = 0; for (int j = 0; j < dof; ++j) d2 = d2 + sq[j]; }                                      \
         else {                                                                                                       \
           d2 = ((sq[0] + sq[1]) + (sq[2] + sq[3])) + ((sq[4] + sq[5]) + (sq[6] + sq[7]));                            \
           for (int j = 8; j < dof; ++j) d2 = d2 + sq[j];                                                             \
         }                                                                                                            \
-        const T d = SQRT(d2);                                                                                        \
-        const int K = (int)(d / (T)rrt_eps);                                              /* :403 */                 \
+        const double d = sqrt(d2);                                                                                   \
+        const int K = (int)(d / rrt_eps);                                                                            \
         for (int k = 0; k < K && ok; ++k) {                                               /* :404-409 */             \
           const T ratio = (T)((double)k * 1. / (double)K);                                                           \
           for (int j = 0; j < dof; ++j) { const T step = ratio * (t[j] - s[j]); qc[j] = (double)(T)(s[j] + step); }  \

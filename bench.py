@@ -372,6 +372,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sub-records", action="store_true", help="only the headline workload (no C3/C4/C5/planner sub-records)")
     ap.add_argument("--sub-steps", type=int, default=5)
+    ap.add_argument("--ef-mode", default="auto", choices=["auto", "tc", "tc4", "simt"], help="edge-feature kernel variant (A/B profiling)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     wl = WORKLOADS[args.workload]
@@ -560,6 +561,8 @@ def run_single(args, wl, rank, local_rank, world):
     model.load_state_dict(torch.load(os.path.join(G, "weights", wl["weights"]), map_location="cpu"))
     model.eval()
     model.set_timing(True)
+    if args.ef_mode != "auto":
+        model.set_edge_feature_mode(args.ef_mode)
 
     # ---- the public batched API (gnn_motion_planning_b200.batch.HotPath) drives both measurements
     from gnn_motion_planning_b200.batch import HotPath

@@ -1456,7 +1456,11 @@ int run_forward(gmp_handle* h, int64_t B, const float* v, const int64_t* edge_in
       tc_detail::unit_meta_kernel<<<(tile_e[B] + 255) / 256, 256, 0, st>>>(ws.tile_ptr_e, (int)B, tile_e[B], ws.edge_ptr, ws.obs_ptr,
                                                                           ws.tc_tab_off, ws.tc_unit_meta);
       GMP_LAUNCH_CHECK();
-      if (m.edge_feature_mode == 2)    // round-1 organisation: four warps per tile, thread == row
+      // auto: eight warps per tile where the first encoder layers are plain FMAs (2c <= 8: maze); four where they are MMA
+      // stages of their own (wider inputs: two more round trips per tile, and the column split does not pay -- measured on
+      // kuka14: 11.2 vs 11.8 ms)
+      const bool four = m.edge_feature_mode == 2 || (m.edge_feature_mode == -1 && !TcCfg<C>::kSimtIn);
+      if (four)                        // round-1 organisation: four warps per tile, thread == row
         edge_feature_tc_kernel<C, 1><<<std::min<int>(tile_e[B], kNumSMs), 384, TcCfg<C>::kSmemBytes, st>>>(
             W + m.w.tc_img, v, ws.csr_src, ws.csr_dst, ws.tc_unit_meta, tile_e[B], ws.tc_tables, tc_stride, use_obstacles, ws.P, ws.Q);
       else                             // eight warps per tile, columns split between warp pairs

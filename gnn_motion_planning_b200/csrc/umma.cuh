@@ -164,40 +164,21 @@ __device__ __forceinline__ float ex2_approx(float x) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// wait for an mbarrier phase.  The poll loop must not eat issue slots: in the first 8-warp version of the edge-feature kernel
-// 30 % of all executed instructions were this loop (17 warps polling while the others had epilogue work to issue).  So the
-// try_wait carries a suspend-time hint (the warp sleeps in hardware until the phase completes or the hint expires) and the
-// hang guard is a TIME bound checked once per 1024 polls: a protocol bug still traps (after ~4 s, instead of hanging the GPU),
-// a long legitimate wait under time-slicing / MPS / a debugger does not.
-#ifndef GMP_MBAR_HINT_NS
-#define GMP_MBAR_HINT_NS 0
-#endif
+// wait for an mbarrier phase.  Bounded: a protocol bug traps instead of hanging the GPU -- but only after 2^30 polls (tens of
+// seconds; round 1 trapped after 2^22, which a long legitimate wait under time-slicing / MPS / a debugger could reach, ADVICE
+// r1).  Measured alternatives (profiles/r2_mbar_wait_sweep.log): a suspend-time hint on try_wait (+0.3 ms on the 8.8 ms
+// edge-feature kernel: coarser wake-up), __nanosleep back-off (no gain: the poll loop is 30 % of the executed instructions
+// but the kernel is bound by the latency of its MMA round trips, not by issue slots), a %globaltimer-based bound (+1-3 %).
 __device__ __forceinline__ void mbar_wait_guard(uint64_t* bar, uint32_t phase) {
   const uint32_t addr = smem_u32(bar);
   uint32_t done = 0, spins = 0;
-  uint64_t t0 = 0;
   while (true) {
-#if GMP_MBAR_HINT_NS > 0
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(done)
-                 : "r"(addr), "r"(phase), "r"((uint32_t)GMP_MBAR_HINT_NS)
-                 : "memory");
-#else
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                  : "=r"(done)
                  : "r"(addr), "r"(phase)
                  : "memory");
-#endif
     if (done) break;
-#if defined(GMP_MBAR_SLEEP_NS) && GMP_MBAR_SLEEP_NS > 0
-    __nanosleep(GMP_MBAR_SLEEP_NS);
-#endif
-    if ((++spins & 1023u) == 0) {
-      uint64_t now;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > 4000000000ull) __trap();
-    }
+    if (++spins > (1u << 30)) __trap();
   }
 }
 

@@ -75,44 +75,58 @@ def result_rows(state, first_problem_id=0):
     return rows
 
 
+class _Stream:
+    """A problem's NumPy RandomState with a read-ahead buffer: draws come out in exactly the order np.random.uniform(-1, 1, 2)
+    calls would produce them; draws that were fetched but not consumed stay queued for the next request (no get_state /
+    set_state rewinds, which cost more than the sampling itself)."""
+
+    def __init__(self, seed):
+        self.rs = np.random.RandomState(int(seed))
+        self.buf = np.zeros((0, 2))
+
+    def peek(self, n):
+        if len(self.buf) < n:
+            self.buf = np.concatenate([self.buf, self.rs.uniform(-LIMITS[:2], LIMITS[:2], (n - len(self.buf), 2))])
+        return self.buf[:n]
+
+    def consume(self, n):
+        self.buf = self.buf[n:]
+
+
 def _sample_batch(rngs, need, maps_d, problem_ids, device):
     """``env.sample_n_points(need[p], need_negative=True)`` (maze_env.py:85-100) for several problems at once: the draws of all
-    problems go through ONE state-check launch per pass; every RandomState ends exactly where the reference's would."""
+    problems go through ONE state-check launch per pass; every stream ends exactly where the reference's would."""
     P = len(rngs)
-    free = [[] for _ in range(P)]
+    free = [[] for _ in range(P)]          # per problem: list of [m,2] float64 chunks, concatenated at the end
     coll = [[] for _ in range(P)]
+    n_got = [0] * P
     counted = np.zeros(P, np.int64)
     todo = [p for p in range(P) if need[p] > 0]
     while todo:
-        states, draws = {}, {}
-        for p in todo:
-            chunk = max(64, int((need[p] - len(free[p])) * 2.5))
-            states[p] = rngs[p].get_state()
-            draws[p] = rngs[p].uniform(-LIMITS[:2], LIMITS[:2], (chunk, 2))
-        allp = np.concatenate([draws[p] for p in todo])
-        prob = np.concatenate([np.full(len(draws[p]), problem_ids[p], np.int32) for p in todo])
+        draws = [rngs[p].peek(max(64, int((need[p] - n_got[p]) * 2.5))) for p in todo]
+        allp = np.concatenate(draws)
+        prob = np.repeat(np.asarray([problem_ids[p] for p in todo], np.int32), [len(d) for d in draws])
         ok = collision.maze_state_fp(torch.from_numpy(allp).to(device), maps_d, torch.from_numpy(prob).to(device)).cpu().numpy().astype(bool)
         off, nxt = 0, []
-        for p in todo:
-            d, f = draws[p], ok[off:off + len(draws[p])]
+        for p, d in zip(todo, draws):
+            f = ok[off:off + len(d)]
             off += len(d)
-            missing = need[p] - len(free[p])
+            missing = need[p] - n_got[p]
             idx = np.flatnonzero(f)
-            used = len(d) if len(idx) < missing else int(idx[missing - 1]) + 1
-            if used < len(d):               # rewind: consume exactly the draws the reference would have made
-                rngs[p].set_state(states[p])
-                d = rngs[p].uniform(-LIMITS[:2], LIMITS[:2], (used, 2))
-                f = f[:used]
+            used = len(d) if len(idx) < missing else int(idx[missing - 1]) + 1      # exactly the draws the reference would make
+            d, f = d[:used], f[:used]
+            rngs[p].consume(used)
             counted[p] += used              # every draw lies inside the limits: one counted lookup each (maze_env.py:272-276)
-            for s_, f_ in zip(d, f):
-                (free[p] if f_ else coll[p]).append(s_)
-            if len(free[p]) < need[p]:
+            free[p].append(d[f])
+            coll[p].append(d[~f])
+            n_got[p] += int(f.sum())
+            if n_got[p] < need[p]:
                 nxt.append(p)
         todo = nxt
-    return free, coll, counted
+    z = np.zeros((0, 2))
+    return [np.concatenate(x) if x else z for x in free], [np.concatenate(x) if x else z for x in coll], counted
 
 
-@torch.no_grad()
 def _sample_batch_device(seed, streams, next_draw, need, maps_d, problem_ids):
     """The same contract through the counter-based device sampler (``gmp_maze_sample_points``): one launch for all problems, no
     host RNG.  ``next_draw`` (per problem) is advanced by the draws consumed."""
@@ -121,8 +135,8 @@ def _sample_batch_device(seed, streams, next_draw, need, maps_d, problem_ids):
     free_d, coll_d, n_coll, n_draws = collision.maze_sample_points(maps_d, problem_ids, streams, n, seed, first_draw=next_draw,
                                                                    cap_collided=16 * n)
     free_h, coll_h, n_coll, n_draws = free_d.cpu().numpy(), coll_d.cpu().numpy(), n_coll.cpu().numpy(), n_draws.cpu().numpy()
-    free = [list(free_h[i]) for i in range(len(streams))]
-    coll = [list(coll_h[i, :min(int(n_coll[i]), coll_h.shape[1])]) for i in range(len(streams))]
+    free = [free_h[i] for i in range(len(streams))]
+    coll = [coll_h[i, :min(int(n_coll[i]), coll_h.shape[1])] for i in range(len(streams))]
     for i in range(len(streams)):
         next_draw[i] += int(n_draws[i])
     return free, coll, n_draws.astype(np.int64)
@@ -130,7 +144,7 @@ def _sample_batch_device(seed, streams, next_draw, need, maps_d, problem_ids):
 
 @torch.no_grad()
 def explore_batch(model, maps, init_states, goal_states, problem_ids, seeds, batch=100, t_max=100, k=10, loop=5, spec_k=1,
-                  device=None, max_checks=20000, sampler="numpy"):
+                  device=None, max_checks=20000, sampler="numpy", timings=None):
     """``explore(env, model, None, smooth=True, batch, t_max, k, smoother='none')`` for every problem of ``problem_ids``
     (rows of ``maps`` / ``init_states`` / ``goal_states``), seeded like ``np.random.seed(seeds[i])`` before the reference call.
 
@@ -140,24 +154,35 @@ def explore_batch(model, maps, init_states, goal_states, problem_ids, seeds, bat
     Returns one dict per problem: success, path (float32 waypoints), path_nodes, explored (node ids in tree order), c_explore
     (= env.collision_check_count delta: sampling + edge + goal-region checks), spec_checks (speculative edge checks that were
     never committed; 0 when spec_k == 1), n_nodes, rounds."""
+    import time as _time
     dev = torch.device(device if device is not None else "cuda")
     P = len(problem_ids)
     problem_ids = [int(p) for p in problem_ids]
+
+    def _tick(name, t0):
+        if timings is not None:                       # phase wall times (synchronised): sample / pack / graph / forward / search
+            torch.cuda.synchronize(dev)
+            timings[name] = timings.get(name, 0.0) + _time.perf_counter() - t0
+        return _time.perf_counter()
     maps_d = torch.as_tensor(np.ascontiguousarray(np.asarray(maps) != 0).astype(np.uint8)).to(dev)
-    rngs = [np.random.RandomState(int(s)) for s in seeds]
+    rngs = [_Stream(s) for s in seeds]
     goal64 = torch.from_numpy(np.ascontiguousarray(np.asarray(goal_states, np.float64)[problem_ids])).to(dev)
     n_batch = batch
     cap_nodes = 2 * (t_max + 2 * n_batch + 2) + 8
     st = TreeSearchState(P, cap_nodes, 2 + 4 * max_checks, dev)
 
     next_draw = [0] * P
+    t0 = _time.perf_counter()
     if sampler == "device":
         new_free, new_coll, counted = _sample_batch_device(0x9E3779B97F4A7C15, list(seeds), next_draw, [n_batch] * P, maps_d, problem_ids)
     else:
         new_free, new_coll, counted = _sample_batch(rngs, [n_batch] * P, maps_d, problem_ids, dev)
-    free = [[np.asarray(init_states[problem_ids[p]]), np.asarray(goal_states[problem_ids[p]])] + new_free[p] for p in range(P)]
+    init_np, goal_np = np.asarray(init_states, np.float64), np.asarray(goal_states, np.float64)
+    free = [np.concatenate([init_np[problem_ids[p]][None], goal_np[problem_ids[p]][None], new_free[p]]) for p in range(P)]
     coll = [new_coll[p][:len(new_free[p])] for p in range(P)]                      # collided = collided[:len(free)] BEFORE init/goal join (:180-181)
     c_sample = counted.copy()
+    t0 = _tick("sample", t0)
+    obs_of = [(np.argwhere(np.asarray(maps[problem_ids[p]]) == 1) / 15.0 - 0.5).astype(np.float32) for p in range(P)]   # maze_env.py:73-79
     active = list(range(P))
     rounds = np.zeros(P, np.int64)
     last_v = [None] * P
@@ -166,22 +191,24 @@ def explore_batch(model, maps, init_states, goal_states, problem_ids, seeds, bat
         # ---- create_data for every active problem (eval_gnn.py:150-165), packed
         vs, n_free, k1 = [], [], []
         for p in active:
-            f = np.asarray(free[p], np.float64).reshape(len(free[p]), 2)
-            c = np.asarray(coll[p], np.float64).reshape(len(coll[p]), 2)
+            f, c = free[p], coll[p]
             vs.append(np.concatenate([f, c]).astype(np.float32))                  # torch.FloatTensor(np.array(...))
             n_free.append(len(f))
             k1.append(graph.k1_of(k, len(f)))
             last_v[p] = vs[-1]
         node_ptr = np.concatenate([[0], np.cumsum([len(x) for x in vs])]).astype(np.int32)
         v_d = torch.from_numpy(np.concatenate(vs)).to(dev)
+        t0 = _tick("pack", t0)
         ei, edge_ptr = graph.knn_graph_batch(v_d, node_ptr, np.asarray(n_free, np.int32), np.asarray(k1, np.int32))
         et = int(edge_ptr[-1])
+        t0 = _tick("graph", t0)
         # ---- model(**data, **obs_data, loop=loop): sparse logits (eval_gnn.py:194)
-        obss = [(np.argwhere(np.asarray(maps[problem_ids[p]]) == 1) / 15.0 - 0.5).astype(np.float32) for p in active]   # maze_env.py:73-79
+        obss = [obs_of[p] for p in active]
         obs_ptr = np.concatenate([[0], np.cumsum([len(o) for o in obss])]).astype(np.int32)
         obs_d = torch.from_numpy(np.concatenate(obss).reshape(-1, 2)).to(dev)
-        goal_d = torch.from_numpy(np.stack([np.asarray(goal_states[problem_ids[p]], np.float32) for p in active])).to(dev)
+        goal_d = torch.from_numpy(goal_np[[problem_ids[p] for p in active]].astype(np.float32)).to(dev)
         logits = model.forward_batch(v_d, ei, goal_d, obs_d, node_ptr, edge_ptr, obs_ptr, loop=loop)
+        t0 = _tick("forward", t0)
         # ---- the search itself
         slots = torch.tensor(active, dtype=torch.int32, device=dev)
         probs = torch.tensor([problem_ids[p] for p in active], dtype=torch.int32, device=dev)
@@ -190,6 +217,7 @@ def explore_batch(model, maps, init_states, goal_states, problem_ids, seeds, bat
                          spec_k=spec_k, first_round=first)
         first = False
         status = st.status.cpu().numpy()
+        t0 = _tick("search", t0)
         nxt = []
         for p in active:
             rounds[p] += 1
@@ -207,9 +235,10 @@ def explore_batch(model, maps, init_states, goal_states, problem_ids, seeds, bat
             else:
                 nf, nc, cnt = _sample_batch([rngs[p] for p in nxt], [n_batch] * len(nxt), maps_d, [problem_ids[p] for p in nxt], dev)
             for i, p in enumerate(nxt):
-                free[p] = free[p] + nf[i]
-                coll[p] = (coll[p] + nc[i])[:len(free[p])]
+                free[p] = np.concatenate([free[p], nf[i]])
+                coll[p] = np.concatenate([coll[p], nc[i]])[:len(free[p])]
                 c_sample[p] += cnt[i]
+            t0 = _tick("sample", t0)
         active = nxt
     # ---- results
     status = st.status.cpu().numpy()

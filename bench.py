@@ -738,7 +738,7 @@ def run_single(args, wl, rank, local_rank, world):
         pass
     traffic = {}
     try:   # DRAM bytes per launch of the two named kernels, from the committed ncu --set full captures (C2 workload only)
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))) if args.workload == "C2" else {}
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json"))) if args.workload == "C2" else {}
     except Exception:
         pass
 
@@ -759,9 +759,10 @@ def run_single(args, wl, rank, local_rank, world):
     if wl["e"] == 32:
         # tcgen05 path: 3xTF32 (three kind::tf32 MMAs per product, fp32 accumulate in TMEM).  TF32 dense runs at half the bf16
         # rate and every product is issued three times, so the ceiling of this arithmetic is peak/6 of the bf16 figure.
-        ef_kernel = "edge_feature_tc_kernel<%d>" % c
+        halves = 1 if (args.ef_mode == "tc4" or (args.ef_mode == "auto" and 2 * c > 8)) else 2     # explorer.cu: auto mode
+        ef_kernel = "edge_feature_tc_kernel<%d,%d>" % (c, halves)
         ef_note = ("tcgen05.mma kind::tf32, 3xTF32 split operands (1e-4 logit tolerance rules out 1-pass TF32/BF16), A operands and "
-                   "accumulators in TMEM; against the 3xTF32 ceiling (bf16 peak / 6 = %.0f TFLOP/s) the fraction is %.3f; the fp32 SIMT "
+                   "accumulators in TMEM; second template argument = epilogue warp groups per 128-edge tile (2: eight warps, columns split); against the 3xTF32 ceiling (bf16 peak / 6 = %.0f TFLOP/s) the fraction is %.3f; the fp32 SIMT "
                    "kernel it replaces peaked at 148 SM x 128 FMA x %.0f MHz = %.1f TFLOP/s"
                    % (peak_tf / 6.0, ef_tflops / (peak_tf / 6.0), sm_mhz, fp32_peak_tf))
     else:

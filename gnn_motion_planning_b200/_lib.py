@@ -38,6 +38,8 @@ SIGNATURES = {
     "gmp_maze_edge_fp": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "gmp_maze_edge_fp_graph": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
                                        c_void_p, c_void_p, c_void_p, c_void_p]),
+    "gmp_maze3_state_fp": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "gmp_maze3_edge_fp": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "gmp_tree_search_workspace_bytes": (c_int64, [c_int64, c_int64, c_int64]),
     "gmp_maze_tree_search": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -93,6 +93,45 @@ def result_rows(logits, edge_free, edge_ptr_d, first_problem_id=0, out=None):
 
 
 @torch.no_grad()
+def maze3_state_fp(states, maps, problem=None):
+    """3-D stick maze states [n,3] f32|f64 cuda -> (free u8 [n], n_checks i32 [n], k i32 [n])   (maze_env.py:279-291)."""
+    _lib.require_cuda(states, "states")
+    if states.dtype not in _DT:
+        raise TypeError("states must be float32 or float64")
+    states = states.reshape(-1, 3).contiguous()
+    maps = maps.to(torch.uint8).contiguous()
+    n = states.shape[0]
+    if problem is not None:
+        problem = problem.to(device=states.device, dtype=torch.int32).contiguous()
+    free = torch.empty(n, dtype=torch.uint8, device=states.device)
+    checks = torch.empty(n, dtype=torch.int32, device=states.device)
+    k = torch.empty(n, dtype=torch.int32, device=states.device)
+    _lib.check(_lib.load().gmp_maze3_state_fp(_lib.ptr(states), _DT[states.dtype], _lib.ptr(maps), _lib.ptr(problem), n, _lib.ptr(free),
+                                              _lib.ptr(checks), _lib.ptr(k), _lib.stream_ptr(states.device)))
+    return free, checks, k
+
+
+@torch.no_grad()
+def maze3_edge_fp(a, b, maps, problem=None):
+    """3-D stick maze edges a, b [n,3] f32|f64 cuda -> (free u8 [n], n_checks i32 [n], k i32 [n])   (maze_env.py:316-347)."""
+    _lib.require_cuda(a, "a")
+    _lib.require_cuda(b, "b")
+    if a.dtype not in _DT or b.dtype != a.dtype:
+        raise TypeError("a and b must both be float32 or both float64")
+    a, b = a.reshape(-1, 3).contiguous(), b.reshape(-1, 3).contiguous()
+    maps = maps.to(torch.uint8).contiguous()
+    n = a.shape[0]
+    if problem is not None:
+        problem = problem.to(device=a.device, dtype=torch.int32).contiguous()
+    free = torch.empty(n, dtype=torch.uint8, device=a.device)
+    checks = torch.empty(n, dtype=torch.int32, device=a.device)
+    k = torch.empty(n, dtype=torch.int32, device=a.device)
+    _lib.check(_lib.load().gmp_maze3_edge_fp(_lib.ptr(a), _lib.ptr(b), _DT[a.dtype], _lib.ptr(maps), _lib.ptr(problem), n, _lib.ptr(free),
+                                             _lib.ptr(checks), _lib.ptr(k), _lib.stream_ptr(a.device)))
+    return free, checks, k
+
+
+@torch.no_grad()
 def maze_sample_points(maps, problem_of_slot, stream_of_slot, n_points, seed, first_draw=None, cap_collided=None):
     """Batched ``env.sample_n_points(n_points, need_negative=True)`` (maze_env.py:85-100) with the counter-based device RNG
     (``gmp_maze_sample_points``): -> (free [S,n,2] f64, collided [S,cap,2] f64, n_collided [S] i32, n_draws [S] i64), all CUDA.

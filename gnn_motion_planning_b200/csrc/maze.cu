@@ -549,6 +549,136 @@ __global__ void __launch_bounds__(32) maze_sample_kernel(const uint8_t* __restri
   }
 }
 
+// =====================================================================================================================
+// 3-D stick maze: MazeEnv(dim=3)                                    (maze_env.py:245-264, 279-291, 327-347)
+// =====================================================================================================================
+// state = (x, y, theta): a stick of length STICK_LENGTH = 0.2 centred at (x, y) at angle theta / 0.4 * pi.  The stick's end
+// points and everything derived from them are float64 in the reference whatever the state dtype (a float32 scalar divided by
+// the float64 LIMITS[2] promotes); poses along an edge are interpolated in the state dtype.  One thread per state / edge,
+// same DFS order and the same collision_check_count / env.k side effects as oracle/maze.c (pinned by
+// tests/golden/maze3_collision.npz, produced by the reference module itself).
+constexpr double kLim2 = 8. * 5e-2;                 // LIMITS[2] = 8 * RRT_EPS (env_config.py)
+constexpr double kStickHalf = (1.5 * 2 / 15) / 2.;  // STICK_LENGTH / 2
+
+// 2-D float64 _edge_fp that also counts its midpoints (env.k); same traversal as edge_free<double>
+__device__ bool edge2_k(const uint8_t* __restrict__ map, double ax, double ay, double bx, double by, int& cnt, int& k, bool endpoints) {
+  if (endpoints) {
+    k = 0;
+    if (!in_range(ax, ay) || !in_range(bx, by)) return false;
+    cnt += 1;
+    if (!cell_free(map, ax, ay)) return false;
+    cnt += 1;
+    if (!cell_free(map, bx, by)) return false;
+  }
+  double lx = ax, ly = ay, rx = bx, ry = by;
+  double sx[kStack], sy[kStack], tx[kStack], ty[kStack];
+  int sp = 0;
+  while (true) {
+    const int dc = abs(cell_of(lx) - cell_of(rx)) + abs(cell_of(ly) - cell_of(ry));
+    const double l1 = fabs(lx - rx) + fabs(ly - ry);
+    if (dc > 1 && l1 > 5e-2 && sp < kStack) {
+      const double mx = (lx + rx) / 2.0, my = (ly + ry) / 2.0;
+      ++k;
+      if (!in_range(mx, my)) return false;     // (a midpoint of two in-range points is in range; kept for symmetry with the reference)
+      ++cnt;
+      if (!cell_free(map, mx, my)) return false;
+      sx[sp] = mx; sy[sp] = my; tx[sp] = rx; ty[sp] = ry;
+      ++sp;
+      rx = mx; ry = my;
+      continue;
+    }
+    if (sp == 0) return true;
+    --sp;
+    lx = sx[sp]; ly = sy[sp]; rx = tx[sp]; ry = ty[sp];
+  }
+}
+
+// explicit roundings: NumPy evaluates a * b + c as two operations; the compiler must not contract them into an FMA here
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+
+template <typename T>
+__device__ __forceinline__ bool valid3(T x, T y, T th) {
+  return in_range(x, y) && (double)th >= -kLim2 && (double)th <= kLim2;
+}
+template <typename T>
+__device__ __forceinline__ void end_points(T x, T y, T th, double& ax, double& ay, double& bx, double& by) {
+  const double theta = (double)th / kLim2 * 3.141592653589793;
+  const double ox = cos(theta), oy = sin(theta);
+  const double hx = __dmul_rn(kStickHalf, ox), hy = __dmul_rn(kStickHalf, oy);      // l / 2. * orient, then centre -/+ that
+  ax = __dsub_rn((double)x, hx); ay = __dsub_rn((double)y, hy);
+  bx = __dadd_rn((double)x, hx); by = __dadd_rn((double)y, hy);
+}
+// _stick_in_free_space (:279-291)
+template <typename T>
+__device__ bool stick_free(const uint8_t* __restrict__ map, T x, T y, T th, int& cnt, int& k) {
+  k = 0;
+  if (!valid3(x, y, th)) return false;
+  double ax, ay, bx, by;
+  end_points(x, y, th, ax, ay, bx, by);
+  if (!in_range(ax, ay)) return false;
+  cnt += 1;
+  if (!cell_free(map, ax, ay)) return false;
+  if (!in_range(bx, by)) return false;
+  cnt += 1;
+  if (!cell_free(map, bx, by)) return false;
+  return edge2_k(map, ax, ay, bx, by, cnt, k, false);
+}
+
+template <typename T> __device__ __forceinline__ T sqrt_rn(T x);
+template <> __device__ __forceinline__ float sqrt_rn<float>(float x) { return __fsqrt_rn(x); }
+template <> __device__ __forceinline__ double sqrt_rn<double>(double x) { return __dsqrt_rn(x); }
+
+template <typename T>
+__global__ void __launch_bounds__(128) maze3_state_kernel(const T* __restrict__ states, const uint8_t* __restrict__ maps,
+                                                          const int32_t* __restrict__ problem, int64_t n, uint8_t* __restrict__ free_out,
+                                                          int32_t* __restrict__ n_checks_out, int32_t* __restrict__ k_out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint8_t* map = maps + (int64_t)(problem ? problem[i] : 0) * (kW * kW);
+    int cnt = 0, k = 0;
+    const bool ok = stick_free<T>(map, states[3 * i], states[3 * i + 1], states[3 * i + 2], cnt, k);
+    free_out[i] = ok ? 1 : 0;
+    if (n_checks_out) n_checks_out[i] = cnt;
+    if (k_out) k_out[i] = k;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) maze3_edge_kernel(const T* __restrict__ a, const T* __restrict__ b, const uint8_t* __restrict__ maps,
+                                                         const int32_t* __restrict__ problem, int64_t n, uint8_t* __restrict__ free_out,
+                                                         int32_t* __restrict__ n_checks_out, int32_t* __restrict__ k_out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint8_t* map = maps + (int64_t)(problem ? problem[i] : 0) * (kW * kW);
+    const T s0 = a[3 * i], s1 = a[3 * i + 1], s2 = a[3 * i + 2], t0 = b[3 * i], t1 = b[3 * i + 1], t2 = b[3 * i + 2];
+    int cnt = 0, k = 0;
+    bool ok = valid3(s0, s1, s2) && valid3(t0, t1, t2);                                            // :320
+    if (ok) ok = stick_free<T>(map, s0, s1, s2, cnt, k) && stick_free<T>(map, t0, t1, t2, cnt, k);   // :322
+    if (ok) {
+      const T d0 = t0 - s0, d1 = t1 - s1;
+      T d2 = t2 - s2;
+      if (fabs((double)d2) > kLim2) d2 = (T)((double)d2 > 0 ? (double)d2 - 2 * kLim2 : (double)d2 + 2 * kLim2);   // :329-333
+      // distance() (:137-149): |diff| per component, the theta component wrapped (computed in float64, stored in T)
+      const T a0 = d0 < 0 ? -d0 : d0, a1 = d1 < 0 ? -d1 : d1;
+      T a2 = (t2 - s2) < 0 ? -(t2 - s2) : (t2 - s2);
+      { const double w = fabs((double)a2 - 2 * kLim2); a2 = (T)((double)a2 < w ? (double)a2 : w); }
+      const T dist = sqrt_rn<T>(add_rn(add_rn(mul_rn(a0, a0), mul_rn(a1, a1)), mul_rn(a2, a2)));
+      const int K = (int)(dist / (T)0.015);                                                          // :337
+      for (int kk = 1; kk < K && ok; ++kk) {
+        const T ratio = (T)((double)kk * 1. / (double)K);
+        const T c0 = add_rn(s0, mul_rn(ratio, d0)), c1 = add_rn(s1, mul_rn(ratio, d1)), c2 = add_rn(s2, mul_rn(ratio, d2));
+        double ax, ay, bx, by;
+        end_points(c0, c1, c2, ax, ay, bx, by);
+        ok = edge2_k(map, ax, ay, bx, by, cnt, k, true);                                             // :344-345
+      }
+    }
+    free_out[i] = ok ? 1 : 0;
+    if (n_checks_out) n_checks_out[i] = cnt;
+    if (k_out) k_out[i] = k;
+  }
+}
+
 // per-problem rows of the final reduction (eval_gnn.py:120-134): (problem id, success, path cost, collision checks of the search,
 // speculative checks never committed, explored nodes) -- the payload of the multi-GPU all-gather
 __global__ void search_rows_kernel(const int32_t* __restrict__ status, const float* __restrict__ path_cost, const int32_t* __restrict__ n_checks,
@@ -705,6 +835,40 @@ extern "C" int gmp_maze_sample_points(const uint8_t* maps, const int32_t* proble
   maze_sample_kernel<<<(unsigned)n_slots, 32, 0, static_cast<cudaStream_t>(stream)>>>(maps, problem_of_slot, stream_of_slot, first_draw, (int)n_slots,
                                                                                      n_points, cap_collided, seed, free_out, collided_out,
                                                                                      n_collided_out, n_draws_out);
+  GMP_LAUNCH_CHECK();
+  return GMP_OK;
+}
+
+extern "C" int gmp_maze3_state_fp(const void* states, int dtype, const uint8_t* maps, const int32_t* problem_of_state, int64_t n,
+                                  uint8_t* free_out, int32_t* n_checks_out, int32_t* k_out, void* stream) {
+  GMP_REQUIRE(n >= 0, "n < 0");
+  GMP_REQUIRE(dtype == GMP_DTYPE_F32 || dtype == GMP_DTYPE_F64, "dtype must be GMP_DTYPE_F32 or GMP_DTYPE_F64");
+  if (n == 0) return GMP_OK;
+  GMP_REQUIRE(states && maps && free_out, "null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == GMP_DTYPE_F32)
+    maze3_state_kernel<float><<<grid_for(n, 128), 128, 0, st>>>(static_cast<const float*>(states), maps, problem_of_state, n, free_out,
+                                                                n_checks_out, k_out);
+  else
+    maze3_state_kernel<double><<<grid_for(n, 128), 128, 0, st>>>(static_cast<const double*>(states), maps, problem_of_state, n, free_out,
+                                                                 n_checks_out, k_out);
+  GMP_LAUNCH_CHECK();
+  return GMP_OK;
+}
+
+extern "C" int gmp_maze3_edge_fp(const void* a, const void* b, int dtype, const uint8_t* maps, const int32_t* problem_of_edge, int64_t n,
+                                 uint8_t* free_out, int32_t* n_checks_out, int32_t* k_out, void* stream) {
+  GMP_REQUIRE(n >= 0, "n < 0");
+  GMP_REQUIRE(dtype == GMP_DTYPE_F32 || dtype == GMP_DTYPE_F64, "dtype must be GMP_DTYPE_F32 or GMP_DTYPE_F64");
+  if (n == 0) return GMP_OK;
+  GMP_REQUIRE(a && b && maps && free_out, "null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == GMP_DTYPE_F32)
+    maze3_edge_kernel<float><<<grid_for(n, 128), 128, 0, st>>>(static_cast<const float*>(a), static_cast<const float*>(b), maps,
+                                                               problem_of_edge, n, free_out, n_checks_out, k_out);
+  else
+    maze3_edge_kernel<double><<<grid_for(n, 128), 128, 0, st>>>(static_cast<const double*>(a), static_cast<const double*>(b), maps,
+                                                                problem_of_edge, n, free_out, n_checks_out, k_out);
   GMP_LAUNCH_CHECK();
   return GMP_OK;
 }

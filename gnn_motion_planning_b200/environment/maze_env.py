@@ -8,14 +8,15 @@ _edge_fp, ...``.  Every collision query -- single (drop-in) or batched -- runs i
 ``csrc/maze.cu`` and reproduces the reference booleans AND its ``collision_check_count`` /
 ``self.k`` side effects bit-for-bit.  There is no CPU fallback.
 
-Only ``dim == 2`` is implemented (the 3-D stick variant is not in any BASELINE config and its
-smoother weights are missing in the reference itself).
+``dim == 2`` is the 2-D point robot of the BASELINE configs; ``dim == 3`` (round 2) is the 3-D stick robot
+(state = x, y, theta; maze_env.py:245-264, 279-291, 327-347) on ``gmp_maze3_state_fp`` / ``gmp_maze3_edge_fp`` --
+its smoother weights are missing in the reference itself, so only ``explore(..., smoother='none')`` runs there.
 """
 import numpy as np
 import torch
 
 from .. import collision
-from .env_config import LIMITS, RRT_EPS
+from .env_config import LIMITS, RRT_EPS, STICK_LENGTH
 
 
 class MazeEnv:
@@ -23,8 +24,8 @@ class MazeEnv:
     voxel_r = 1. / 15
 
     def __init__(self, dim=2, map_file=None, device=None):
-        if dim != 2:
-            raise NotImplementedError("only the 2-D maze is implemented on the B200 path (SURVEY.md section 8, a7)")
+        if dim not in (2, 3):
+            raise NotImplementedError("MazeEnv: dim must be 2 (point robot) or 3 (stick robot)")
         self.dim = dim
         self.config_dim = dim
         self.collision_check_count = 0
@@ -38,7 +39,7 @@ class MazeEnv:
         self.width = self.maps.shape[1]
         if self.width != 15:
             raise NotImplementedError("the maze kernels are specialised for 15x15 maps")
-        self.bound = (-1, -1, 1, 1)
+        self.bound = (-1, -1, 1, 1) if dim == 2 else (-1, -1, -0.4, 1, 1, 0.4)      # maze_env.py:30-33
         self.order = list(range(self.size))
         self.episode_i = 0
         self.collision_point = None
@@ -92,13 +93,15 @@ class MazeEnv:
             state = np.random.get_state()
             draws = np.random.uniform(-LIMITS[:self.dim], LIMITS[:self.dim], (chunk, self.dim))
             free = self.state_fp_batch(draws, count=False)
+            checks = self._last_state_checks
             idx = np.flatnonzero(free)
             used = chunk if len(idx) < need else int(idx[need - 1]) + 1
             if used < chunk:  # rewind and consume exactly `used` draws
                 np.random.set_state(state)
                 draws = np.random.uniform(-LIMITS[:self.dim], LIMITS[:self.dim], (used, self.dim))
                 free = free[:used]
-            self.collision_check_count += used       # every draw is in range -> one counted lookup each
+            # 2-D: every draw is in range -> one counted lookup each; 3-D: the lookups of each consumed stick check
+            self.collision_check_count += int(checks[:used].sum())
             for s, f in zip(draws, free):
                 (samples if f else negative).append(s)
             need = n - len(samples)
@@ -112,10 +115,46 @@ class MazeEnv:
         diff = np.abs(np.asarray(to_state) - np.asarray(from_state))
         if diff.ndim == 1:
             diff = diff.reshape(1, -1)
+        if self.dim >= 3:                                    # theta wraps (maze_env.py:145-147)
+            diff[:, 2] = np.min((diff[:, 2], np.abs(diff[:, 2] - 2 * LIMITS[2])), axis=0)
         return np.sqrt(np.sum(diff ** 2, axis=-1))
 
     def interpolate(self, from_state, to_state, ratio):
-        return from_state + (to_state - from_state) * ratio
+        diff = to_state - from_state
+        if self.dim >= 3:                                    # maze_env.py:154-160
+            if np.abs(diff[2]) > LIMITS[2]:
+                if diff[2] > 0:
+                    diff[2] -= 2 * LIMITS[2]
+                else:
+                    diff[2] += 2 * LIMITS[2]
+        new_state = from_state + diff * ratio
+        if self.dim >= 3:                                    # maze_env.py:164-170
+            if np.abs(new_state[2]) > LIMITS[2]:
+                if new_state[2] > 0:
+                    new_state[2] -= 2 * LIMITS[2]
+                else:
+                    new_state[2] += 2 * LIMITS[2]
+        return new_state
+
+    @staticmethod
+    def _end_points(coord=None, l=None, center=None, theta=None, a=None, b=None):
+        """maze_env.py:245-264 (host helper for plots; the collision kernels compute the end points themselves)."""
+        if theta is None:
+            theta = coord[2] / LIMITS[2] * np.pi
+        orient = np.array([np.cos(theta), np.sin(theta)])
+        if l is None:
+            l = STICK_LENGTH
+        if a is None and b is None:
+            if center is None:
+                center = np.array(coord[:2])
+            a = center - l / 2. * orient
+            b = center + l / 2. * orient
+        else:
+            if a is not None:
+                b = a + l * orient
+            if b is not None:
+                a = b - l * orient
+        return a, b
 
     def in_goal_region(self, state):
         return bool(self.distance(state, self.goal_state) < RRT_EPS and self._state_fp(state))
@@ -141,27 +180,42 @@ class MazeEnv:
                 for x in range(self.map.shape[0]) for y in range(self.map.shape[1]) if self.map[x, y] == 0]
 
     # ------------------------------------------------------------------ collision: batched (new) ...
-    def _to_dev(self, x):
+    def _to_dev(self, x, width=2):
         x = np.ascontiguousarray(x)
         if x.dtype not in (np.float32, np.float64):
             x = x.astype(np.float64)
-        return torch.from_numpy(x.reshape(-1, 2)).to(self.device)
+        return torch.from_numpy(x.reshape(-1, width)).to(self.device)
 
     def state_fp_batch(self, states, count=True):
-        """bool[n] for n states against the current problem; advances collision_check_count like n _state_fp calls."""
-        s = self._to_dev(states)
+        """bool[n] for n states against the current problem; advances collision_check_count like n _state_fp calls.
+        States are 2-D points, or (dim == 3 and 3 columns) sticks."""
+        width = 3 if (self.dim == 3 and np.asarray(states).shape[-1] == 3) else 2
+        s = self._to_dev(states, width)
         prob = torch.full((s.shape[0],), self._problem, dtype=torch.int32, device=self.device)
-        free, counted = collision.maze_state_fp(s, self._maps_d, prob, want_counted=True)
+        if width == 3:
+            free, checks, k = collision.maze3_state_fp(s, self._maps_d, prob)
+            checks = checks.cpu().numpy()
+            self._last_k = k.cpu().numpy()
+        else:
+            free, counted = collision.maze_state_fp(s, self._maps_d, prob, want_counted=True)
+            checks = counted.cpu().numpy().astype(np.int64)
+        self._last_state_checks = checks
         if count:
-            self.collision_check_count += int(counted.sum())
+            self.collision_check_count += int(checks.sum())
         return free.cpu().numpy().astype(bool)
 
     def edge_fp_batch(self, a, b, count=True):
         """bool[n] for n edges against the current problem; advances collision_check_count like n _edge_fp calls."""
-        a_d = self._to_dev(a)
-        b_d = self._to_dev(np.asarray(b, dtype=np.asarray(a).dtype if np.asarray(a).dtype in (np.float32, np.float64) else np.float64))
+        width = 3 if (self.dim == 3 and np.asarray(a).shape[-1] == 3) else 2
+        a_d = self._to_dev(a, width)
+        b_d = self._to_dev(np.asarray(b, dtype=np.asarray(a).dtype if np.asarray(a).dtype in (np.float32, np.float64) else np.float64), width)
         prob = torch.full((a_d.shape[0],), self._problem, dtype=torch.int32, device=self.device)
-        free, checks = collision.maze_edge_fp(a_d, b_d, self._maps_d, prob, want_checks=True)
+        if width == 3:
+            free, checks, k = collision.maze3_edge_fp(a_d, b_d, self._maps_d, prob)
+            self._last_k = k.cpu().numpy()
+        else:
+            free, checks = collision.maze_edge_fp(a_d, b_d, self._maps_d, prob, want_checks=True)
+            self._last_k = None
         checks = checks.cpu().numpy()
         if count:
             self.collision_check_count += int(checks.sum())
@@ -181,15 +235,30 @@ class MazeEnv:
             self.collision_point = state
         return free
 
+    def _stick_in_free_space(self, state):
+        state = np.asarray(state)
+        assert state.size == 3
+        free = bool(self.state_fp_batch(state.reshape(1, 3))[0])
+        self.k = int(self._last_k[0])
+        if not free and self._valid_state(state):
+            self.collision_point = state
+        return free
+
     def _state_fp(self, state):
-        return self._point_in_free_space(state)
+        state = np.asarray(state)
+        assert state.size == 2 or state.size == 3
+        return self._point_in_free_space(state) if state.size == 2 else self._stick_in_free_space(state)
 
     def _edge_fp(self, state, new_state):
         state, new_state = np.asarray(state), np.asarray(new_state)
-        assert state.size == new_state.size == 2
+        assert state.size == new_state.size and state.size in (2, 3)
         if new_state.dtype != state.dtype:
             common = np.result_type(state.dtype, new_state.dtype)
             state, new_state = state.astype(common), new_state.astype(common)
+        if state.size == 3:                                  # stick robot (maze_env.py:327-347)
+            free = bool(self.edge_fp_batch(state.reshape(1, 3), new_state.reshape(1, 3))[0])
+            self.k = int(self._last_k[0])
+            return free
         free = bool(self.edge_fp_batch(state.reshape(1, 2), new_state.reshape(1, 2))[0])
         # self.k = number of bisection midpoints (maze_env.py:308): lookups minus the two endpoint lookups
         self.k = max(int(self._last_checks[0]) - 2, 0)

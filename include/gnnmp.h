@@ -142,6 +142,16 @@ int gmp_maze_edge_fp_graph(const float* v, const int64_t* edge_index, int64_t ed
                            int64_t n_edges_total, const uint8_t* maps, uint8_t* free_out, int32_t* n_checks_out,
                            void* stream);
 
+/* ---- 3-D stick maze: MazeEnv(dim=3) (environment/maze_env.py:245-264, 279-291, 327-347) ------ */
+/* states [n,3] = (x, y, theta) f32|f64.  _state_fp = _stick_in_free_space: valid state, both stick end points free, bisection of
+ * the stick (float64 geometry whatever the state dtype).  _edge_fp: both states, then K = int(distance / 0.015) interpolated poses
+ * (theta wrapped), each stick checked as a 2-D edge.  n_checks_out = collision_check_count increments, k_out = env.k afterwards
+ * (both nullable). */
+int gmp_maze3_state_fp(const void* states, int dtype, const uint8_t* maps, const int32_t* problem_of_state, int64_t n,
+                       uint8_t* free_out, int32_t* n_checks_out, int32_t* k_out, void* stream);
+int gmp_maze3_edge_fp(const void* a, const void* b, int dtype, const uint8_t* maps, const int32_t* problem_of_edge, int64_t n,
+                      uint8_t* free_out, int32_t* n_checks_out, int32_t* k_out, void* stream);
+
 /* ---- batched lazy tree search: the inner loop of explore() (eval_gnn.py:198-233), maze environments ------------ */
 /* One CTA per problem replays the reference's search on the SPARSE logits of gmp_explorer_forward: masks of eval_gnn.py:198-202
  * (diagonal, explored columns, collided rows / columns = nodes >= n_free[g], the explored-edge list with the reference's

@@ -495,6 +495,78 @@ def more_goldens():
     cg["ids"] = np.array([2000, 2003])
     np.savez_compressed(os.path.join(HERE, "construct_graph.npz"), **cg)
 
+    # ---------------------------------------------------------------- 3-D stick maze (maze_env.py:245-264, 279-291, 327-347)
+    # MazeEnv(dim=3): state = (x, y, theta), a stick of length 0.2 centred at (x, y); _state_fp = both end points free + the
+    # bisection of the stick; _edge_fp = K = int(d / 0.015) interpolated poses, each stick checked as a 2-D edge.
+    env3 = MazeEnv(dim=3)
+    ids3 = np.array([0, 1, 2, 5, 2000, 2001, 2002, 2003])
+    m3 = {"ids": ids3, "maps": env3.maps[ids3].astype(np.uint8), "init_states": env3.init_states[ids3],
+          "goal_states": env3.goal_states[ids3]}
+    rng3 = np.random.default_rng(333)
+    for dt in (np.float32, np.float64):
+        S, SP, SF, SC, SK = [], [], [], [], []
+        A, B, EP, EF, EC, EK = [], [], [], [], [], []
+        for pi, pid in enumerate(ids3):
+            env3.init_new_problem(int(pid))
+            st = np.concatenate([rng3.uniform(-1.05, 1.05, (250, 2)), rng3.uniform(-0.42, 0.42, (250, 1))], 1)
+            st = np.concatenate([st, [[0, 0, 0.4], [0, 0, -0.4], [1, 1, 0], [-1, -1, 0.2], [0.5, 0.5, 0.40000001]]]).astype(dt)
+            for s_ in st:
+                c0 = env3.collision_check_count
+                f = bool(env3._state_fp(s_))
+                S.append(s_); SP.append(pi); SF.append(f); SC.append(env3.collision_check_count - c0); SK.append(env3.k)
+            np.random.seed(900 + int(pid))
+            free = np.array(env3.sample_n_points(60)).astype(dt)
+            pairs = []
+            d = ((free[:, None, :2] - free[None, :, :2]) ** 2).sum(-1)
+            nn = np.argsort(d, axis=1)[:, :4]
+            for i in range(len(free)):
+                for j in nn[i]:
+                    pairs.append((free[i], free[j]))
+            for _ in range(60):
+                i, j = rng3.integers(0, len(free), 2)
+                pairs.append((free[i], free[j]))
+            for _ in range(20):                                   # theta wrap-around (|dtheta| > 0.4) and out-of-range states
+                i = rng3.integers(0, len(free))
+                q = free[i].copy(); q[2] = -q[2] if abs(q[2]) > 0.25 else (0.39 if q[2] < 0 else -0.39)
+                pairs.append((free[i], q.astype(dt)))
+                pairs.append((free[i], (free[i] + np.array([0.03, -0.02, 0.9])).astype(dt)))
+            for a_, b_ in pairs:
+                c0 = env3.collision_check_count
+                f = bool(env3._edge_fp(a_.copy(), b_.copy()))
+                A.append(a_); B.append(b_); EP.append(pi); EF.append(f)
+                EC.append(env3.collision_check_count - c0); EK.append(env3.k)
+        tag = "f32" if dt == np.float32 else "f64"
+        m3.update({"states_" + tag: np.array(S, dt), "state_problem_" + tag: np.array(SP, np.int32),
+                   "state_free_" + tag: np.array(SF, np.uint8), "state_checks_" + tag: np.array(SC, np.int32),
+                   "state_k_" + tag: np.array(SK, np.int32),
+                   "edge_a_" + tag: np.array(A, dt), "edge_b_" + tag: np.array(B, dt), "edge_problem_" + tag: np.array(EP, np.int32),
+                   "edge_free_" + tag: np.array(EF, np.uint8), "edge_checks_" + tag: np.array(EC, np.int32),
+                   "edge_k_" + tag: np.array(EK, np.int32)})
+        print("maze3", tag, len(S), "states free", np.mean(SF), len(A), "edges free", np.mean(EF), "mean checks", np.mean(EC))
+    np.savez_compressed(os.path.join(HERE, "maze3_collision.npz"), **m3)
+
+    # ---------------------------------------------------------------- explore() on the 3-D stick maze (str2name 'maze3', smoother='none')
+    m3x = ref_model.EncoderProcessDecoder(workspace_size=2, config_size=3, embed_size=32, obs_size=2)
+    m3x.load_state_dict(torch.load(os.path.join(REF, "data/weights/weights_maze_3.pt"), map_location="cpu"))
+    m3x.eval()
+    ref_forward3 = m3x.forward
+    m3x.forward = lambda *a, **k: ref_forward3(*a, **k).as_subclass(LegacyIndexTensor)
+    ns["model_smooth"] = ns_s["model_smooth"]
+    e3 = {}
+    ids = [2000, 2001, 2002, 2003]
+    for pid in ids:
+        np.random.seed(31 + pid)
+        env3.init_new_problem(pid)
+        r = ns["explore"](env3, m3x, None, smooth=True, batch=100, t_max=300, k=10, smoother="none")
+        e3["p%d_success" % pid] = np.array(r["success"])
+        e3["p%d_c_explore" % pid] = np.array(r["c_explore"])
+        e3["p%d_explored" % pid] = np.array(r["explored"])
+        e3["p%d_path" % pid] = np.array(r["path"]) if r["success"] else np.zeros((0, 3), np.float32)
+        e3["p%d_n_nodes" % pid] = np.array(len(r["data"].v))
+        print("explore maze3", pid, r["success"], r["c_explore"], len(r["explored"]), len(r["data"].v))
+    e3["ids"] = np.array(ids)
+    np.savez_compressed(os.path.join(HERE, "explore_maze3.npz"), **e3)
+
 
 if __name__ == "__main__":
     if "--more-only" not in sys.argv:

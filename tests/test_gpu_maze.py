@@ -135,3 +135,42 @@ def test_construct_graph_golden(cuda_device):
         assert np.array_equal(np.array([len(neighbors[i]) for i in range(len(pts))]), gold[tag + "_deg"])
         assert np.array_equal(np.concatenate([np.asarray(neighbors[i], np.int64) for i in range(len(pts))]), gold[tag + "_nbr_flat"])
         assert np.array_equal(np.concatenate([np.asarray(edge_cost[i], np.float64) for i in range(len(pts))]), gold[tag + "_cost_flat"])
+
+
+@pytest.mark.parametrize("t", ["f32", "f64"])
+def test_maze3_stick_golden(cuda_device, t):
+    """gmp_maze3_state_fp / gmp_maze3_edge_fp against the reference's own MazeEnv(dim=3): booleans, check counts and env.k."""
+    from gnn_motion_planning_b200 import collision
+    g = np.load(os.path.join(G, "maze3_collision.npz"))
+    dev = cuda_device
+    maps = torch.from_numpy(g["maps"]).to(dev)
+    f, c, k = collision.maze3_state_fp(torch.from_numpy(g["states_" + t]).to(dev), maps, torch.from_numpy(g["state_problem_" + t]).to(dev))
+    assert np.array_equal(f.cpu().numpy(), g["state_free_" + t])
+    assert np.array_equal(c.cpu().numpy(), g["state_checks_" + t]) and np.array_equal(k.cpu().numpy(), g["state_k_" + t])
+    f, c, k = collision.maze3_edge_fp(torch.from_numpy(g["edge_a_" + t]).to(dev), torch.from_numpy(g["edge_b_" + t]).to(dev), maps,
+                                      torch.from_numpy(g["edge_problem_" + t]).to(dev))
+    assert np.array_equal(f.cpu().numpy(), g["edge_free_" + t])
+    assert np.array_equal(c.cpu().numpy(), g["edge_checks_" + t]) and np.array_equal(k.cpu().numpy(), g["edge_k_" + t])
+
+
+def test_maze3_stick_vs_oracle_large(cuda_device):
+    """200 000 random edges / states per dtype against the C oracle (device cos / sin vs libm: the stick end points may differ in
+    the last bit, which can only matter on a cell boundary -- none may show up here)."""
+    from gnn_motion_planning_b200 import collision
+    from oracle import maze as o_maze
+    g = np.load(os.path.join(G, "maze3_collision.npz"))
+    rng = np.random.default_rng(12)
+    n = 200000
+    for dt in (np.float32, np.float64):
+        a = np.concatenate([rng.uniform(-1, 1, (n, 2)), rng.uniform(-0.4, 0.4, (n, 1))], 1).astype(dt)
+        b = (a + np.concatenate([rng.normal(0, 0.08, (n, 2)), rng.normal(0, 0.15, (n, 1))], 1)).astype(dt)
+        b[:, 2] = np.clip(b[:, 2], -0.4, 0.4)
+        pr = rng.integers(0, len(g["maps"]), n).astype(np.int32)
+        dev = cuda_device
+        maps = torch.from_numpy(g["maps"]).to(dev)
+        f, c, k = collision.maze3_edge_fp(torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev), maps, torch.from_numpy(pr).to(dev))
+        of, oc, ok = o_maze.stick_edge_fp(a, b, g["maps"], pr)
+        assert np.array_equal(f.cpu().numpy(), of) and np.array_equal(c.cpu().numpy(), oc) and np.array_equal(k.cpu().numpy(), ok)
+        f, c, k = collision.maze3_state_fp(torch.from_numpy(a).to(dev), maps, torch.from_numpy(pr).to(dev))
+        of, oc, ok = o_maze.stick_state_fp(a, g["maps"], pr)
+        assert np.array_equal(f.cpu().numpy(), of) and np.array_equal(c.cpu().numpy(), oc)

@@ -129,3 +129,15 @@ def test_smoother_oracle_matches_reference(tag, wfile):
         assert np.abs(got - want).max() < 1e-5
         assert np.array_equal(got[0], sm[tag + "_path"][0]) and np.array_equal(got[-1], sm[tag + "_path"][-1])
     assert torch.equal(smoother.chain_edge_index(len(sm[tag + "_path"])), torch.from_numpy(sm[tag + "_edge_index"]))
+
+
+@pytest.mark.parametrize("t", ["f32", "f64"])
+def test_maze3_stick_oracle_matches_reference(t):
+    """3-D stick maze (MazeEnv(dim=3), maze_env.py:245-264,279-291,327-347): booleans, collision_check_count and env.k of the
+    reference module itself, float32 and float64 states (theta wrap-around and out-of-range states included)."""
+    g = np.load(os.path.join(G, "maze3_collision.npz"))
+    f, c, k = maze.stick_state_fp(g["states_" + t], g["maps"], g["state_problem_" + t])
+    assert np.array_equal(f, g["state_free_" + t]) and np.array_equal(c, g["state_checks_" + t]) and np.array_equal(k, g["state_k_" + t])
+    f, c, k = maze.stick_edge_fp(g["edge_a_" + t], g["edge_b_" + t], g["maps"], g["edge_problem_" + t])
+    assert np.array_equal(f, g["edge_free_" + t]) and np.array_equal(c, g["edge_checks_" + t]) and np.array_equal(k, g["edge_k_" + t])
+    assert 0.3 < f.mean() < 0.7 and c.max() > 100

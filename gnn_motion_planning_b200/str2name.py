@@ -10,6 +10,9 @@ from .model_smoother import ModelSmoother
 # name -> (workspace_size, config_size, explorer embed, obs_size, explorer weights, smoother weights, data path)
 TABLE = {
     "maze2": (2, 2, 32, 2, "data/weights/weights_maze.pt", "data/weights/smooth_2d_attv3.pt", "data/pkl/maze_prm_4000.pkl"),
+    # maze3: the reference's smoother file smooth_3d_attv3.pt is not shipped (only smooth_3d_att.pt, another architecture), so
+    # load=True fails there as it does in the reference; the explorer + MazeEnv(dim=3) run with smoother='none'
+    "maze3": (2, 3, 32, 2, "data/weights/weights_maze_3.pt", "data/weights/smooth_3d_attv3.pt", "data/pkl/maze_prm_3.pkl"),
     "kuka7": (3, 7, 64, 6, "data/weights/weights_kuka.pt", "data/weights/smooth_7d_attv3.pt", "data/pkl/kuka_prm_4000.pkl"),
     "ur5": (3, 6, 32, 6, "data/weights/weights_ur5.pt", "data/weights/smooth_ur5_attv3.pt", "data/pkl/ur5_prm_3000.pkl"),
     "snake7": (3, 7, 32, 2, "data/weights/weights_snake.pt", "data/weights/smooth_snake_attv3.pt", "data/pkl/snake_prm_3000.pkl"),
@@ -21,6 +24,8 @@ TABLE = {
 def _make_env(name, **env_kwargs):
     if name == "maze2":
         return MazeEnv(dim=2, **env_kwargs)
+    if name == "maze3":
+        return MazeEnv(dim=3, **env_kwargs)
     if name == "kuka7":
         return KukaEnv(**env_kwargs)
     if name == "kuka13":
@@ -37,7 +42,7 @@ def _make_env(name, **env_kwargs):
 def str2name(str, get_data=False, use_obstacle=True, load=False, make_env=True, **env_kwargs):
     key = "maze2" if "maze2" in str else str          # reference: `if 'maze2' in str` (str2name.py:12)
     if key not in TABLE:
-        raise KeyError("unknown environment %r; known: %s (maze3 is not runnable in the reference either)" % (str, sorted(TABLE)))
+        raise KeyError("unknown environment %r; known: %s" % (str, sorted(TABLE)))
     ws, c, e, s, explore_path, smooth_path, data_path = TABLE[key]
     device = torch.device("cuda", torch.cuda.current_device())
     env = _make_env(key, **env_kwargs) if make_env else None

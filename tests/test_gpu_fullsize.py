@@ -99,8 +99,9 @@ def test_str2name_factory(cuda_device):
         assert model_s.config_size == c and model_s.embed_size == 128
         assert mp.startswith("data/weights/") and sp.startswith("data/weights/")
     assert str2name("ur5", make_env=False)[3].scale == pytest.approx(2 * np.pi)
+    assert str2name("maze3", make_env=False)[1].config_size == 3                  # runnable with smoother='none' (round 2)
     with pytest.raises(KeyError):
-        str2name("maze3", make_env=False)
+        str2name("maze4", make_env=False)
 
 
 def test_hotpath_submit_wait_matches_compute(cuda_device):

@@ -87,7 +87,7 @@ def run_mixed(args, wl, rank, local_rank, world):
     problems; a step = all five sub-batches (graph build + forward + all-edge collision check each)."""
     import torch
     import torch.distributed as dist
-    from gnn_motion_planning_b200 import _lib, collision
+    from gnn_motion_planning_b200 import _lib, collision, shard
     from gnn_motion_planning_b200.batch import HotPath
     from gnn_motion_planning_b200.model import EncoderProcessDecoder
     _lib.load()
@@ -147,7 +147,7 @@ def run_mixed(args, wl, rank, local_rank, world):
             bufs = s["hp"].compute(s["dev_in"][0], s["dev_in"][1], s["dev_in"][2], s["obs_ptr"], s["dev_in"][3])
             b.record()
             if world > 1:
-                dist.all_gather_into_tensor(s.setdefault("gather", torch.empty((world * s["B"], 4), device=dev)), bufs["rows"])
+                shard.gather_result_rows(bufs["rows"], out=s.setdefault("gather", torch.empty((world * s["B"], 4), device=dev)), equal_shards=True)
             if timed:
                 b.synchronize()
                 per_env_ms[s["env"]] = per_env_ms.get(s["env"], 0.0) + a.elapsed_time(b)
@@ -488,6 +488,11 @@ def run_planner(args, rank, local_rank, world):
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         out[spec_k] = (float(dt), res)
+    # the only collective of the planner run: the per-problem rows (id, success, path cost, checks, ...) of eval_gnn.py:120-134
+    from gnn_motion_planning_b200 import shard
+    rows_local = torch.tensor(np.stack([r["row"] for r in out[1][1]]), dtype=torch.float32, device=dev)
+    rows_local[:, 0] += rank * P
+    summary = shard.summarize_search(shard.gather_result_rows(rows_local, equal_shards=True))
     tm = {}
     search.explore_batch(model, maps, init, goal, ids, seeds, batch=100, t_max=100, k=10, spec_k=1, device=dev, timings=tm)
     tmd = {}
@@ -517,7 +522,7 @@ def run_planner(args, rank, local_rank, world):
         "metric": "planner_problems_per_sec", "value": P * world / dt, "unit": "problems/s", "n_gpus": world, "wall_s": dt,
         "config": {"workload": "C1 batched: explore(batch=100, t_max=100, k=10, smoother='none') x %d maze problems/GPU (maze_maps_256.npz maps, "
                                "seeded init/goal), sampling + create_data + forward + lazy tree search all batched" % P},
-        "success": sum(r["success"] for r in res), "problems": P,
+        "success": sum(r["success"] for r in res), "problems": P, "all_ranks": summary,
         "mean_collision_checks": float(np.mean([r["c_explore"] for r in res])), "mean_explored": float(np.mean([len(r["explored"]) for r in res])),
         "spec_k8": {"value": P * world / out[8][0], "unit": "problems/s", "uncommitted_speculative_checks_per_problem": float(np.mean([r["spec_checks"] for r in out[8][1]])),
                     "identical_results": all(a["explored"] == b["explored"] and a["c_explore"] == b["c_explore"] for a, b in zip(res, out[8][1]))},
@@ -550,7 +555,7 @@ class _SyntheticMazeEnv:
 def run_single(args, wl, rank, local_rank, world):
     import torch
     import torch.distributed as dist
-    from gnn_motion_planning_b200 import _lib, collision, graph
+    from gnn_motion_planning_b200 import _lib, collision, graph, shard
     from gnn_motion_planning_b200.model import EncoderProcessDecoder
     dev = torch.device("cuda", local_rank)
 
@@ -624,7 +629,7 @@ def run_single(args, wl, rank, local_rank, world):
         evs = [ev() for _ in range(4)]
         bufs = hp.compute(v_d, goal_d, obs_d, obs_ptr, prob_d, events=evs)
         if world > 1:   # the only collective: per-problem result rows
-            dist.all_gather_into_tensor(gather_buf.view(world * B, 4), bufs["rows"])
+            shard.gather_result_rows(bufs["rows"], out=gather_buf.view(world * B, 4), equal_shards=True)
         state.update(et=bufs["et"], edge_ptr=bufs["edge_ptr"], rows=bufs["rows"], checks=bufs["checks"], bufs=bufs)
         if sm is not None:
             se = (ev(), ev())
@@ -682,7 +687,7 @@ def run_single(args, wl, rank, local_rank, world):
         if sm is not None:
             state["smooth_path"] = run_smoother()
         if world > 1:
-            dist.all_gather_into_tensor(gather_buf.view(world * B, 4), t["rows"])
+            shard.gather_result_rows(t["rows"], out=gather_buf.view(world * B, 4), equal_shards=True)
         pending.append(t)
         if len(pending) > 1:
             res = HotPath.wait(pending.pop(0))          # the host owns step k-1's results from here on

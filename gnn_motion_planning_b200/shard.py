@@ -30,12 +30,22 @@ def balanced_shards(costs, world):
     return np.array(bounds, dtype=np.int64)
 
 
-def gather_result_rows(rows, group=None):
+def gather_result_rows(rows, group=None, out=None, equal_shards=False):
     """All-gather the per-problem result rows [n_local, W] of every rank -> [n_total, W], ordered by rank (= by
-    problem id for contiguous shards).  Shards may have different sizes: rows are padded to the largest shard."""
+    problem id for contiguous shards).  Shards may have different sizes: rows are padded to the largest shard.
+    equal_shards=True (every rank holds the same number of rows, e.g. the weak-scaling bench): ONE collective straight into
+    `out` ([world * n_local, W], allocated if None), no size exchange, no host synchronisation."""
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
         return rows
     world = dist.get_world_size(group)
+    if equal_shards:
+        if out is None:
+            out = rows.new_empty((world * rows.shape[0], rows.shape[1]))
+        if rows.is_cuda:
+            dist.all_gather_into_tensor(out, rows.contiguous(), group=group)
+        else:
+            dist.all_gather(list(out.view(world, rows.shape[0], rows.shape[1]).unbind(0)), rows.contiguous(), group=group)
+        return out
     n_local = torch.tensor([rows.shape[0]], dtype=torch.int64, device=rows.device)
     counts = [torch.zeros_like(n_local) for _ in range(world)]
     dist.all_gather(counts, n_local, group=group)
@@ -57,3 +67,12 @@ def summarize(rows):
     """The reduction of eval_gnn.py:128-134 on gathered rows (problem id, E_g, #free edges, best logit)."""
     return {"n_problems": int(rows.shape[0]), "edges_total": float(rows[:, 1].sum()), "free_edges_total": float(rows[:, 2].sum()),
             "best_logit_mean": float(rows[:, 3].mean()) if rows.shape[0] else 0.0}
+
+
+def summarize_search(rows):
+    """The reduction of eval_gnn.py:128-134 on gathered planner rows (problem id, success, path cost, search checks, uncommitted
+    speculative checks, explored nodes) -- `search.result_rows`."""
+    ok = rows[:, 1] > 0
+    n_ok = int(ok.sum())
+    return {"n_problems": int(rows.shape[0]), "n_success": n_ok, "collision_checks_mean": float(rows[:, 3].mean()) if rows.shape[0] else 0.0,
+            "path_cost_mean": float(rows[ok, 2].mean()) if n_ok else 0.0, "speculative_checks_mean": float(rows[:, 4].mean()) if rows.shape[0] else 0.0}

@@ -33,7 +33,8 @@ def _worker(rank, world, port, n_problems, q):
     try:
         lo, hi = shard.shard_range(n_problems, rank, world)
         rows = _fake_rows(lo, hi)
-        allrows = shard.gather_result_rows(rows)
+        equal = n_problems % world == 0          # equal shards: the single-collective fast path the bench uses
+        allrows = shard.gather_result_rows(rows, equal_shards=equal)
         q.put((rank, lo, hi, allrows.numpy()))
     finally:
         dist.destroy_process_group()
@@ -75,3 +76,10 @@ def test_partitions():
     per = [costs[b[i]:b[i + 1]].sum() for i in range(4)]
     assert max(per) - min(per) <= 3.5 * 2
     assert np.array_equal(shard.balanced_shards(np.ones(8), 8), np.arange(9))
+
+
+def test_summarize_search_rows():
+    # (problem id, success, path cost, search checks, uncommitted speculative checks, explored nodes): eval_gnn.py:128-134
+    rows = torch.tensor([[0, 1, 2.0, 100, 3, 20], [1, 0, 0.0, 300, 9, 80], [2, 1, 4.0, 200, 0, 40]], dtype=torch.float32)
+    s_ = shard.summarize_search(rows)
+    assert s_ == {"n_problems": 3, "n_success": 2, "collision_checks_mean": 200.0, "path_cost_mean": 3.0, "speculative_checks_mean": 4.0}

@@ -80,22 +80,27 @@ class _Stream:
     calls would produce them; draws that were fetched but not consumed stay queued for the next request (no get_state /
     set_state rewinds, which cost more than the sampling itself)."""
 
-    def __init__(self, seed):
+    def __init__(self, seed, lo=None, hi=None):
         self.rs = np.random.RandomState(int(seed))
-        self.buf = np.zeros((0, 2))
+        self.lo = -LIMITS[:2] if lo is None else np.asarray(lo, np.float64)      # maze: uniform(-LIMITS, LIMITS) (maze_env.py:131)
+        self.hi = LIMITS[:2] if hi is None else np.asarray(hi, np.float64)       # arms: uniform(pose_range) (kuka_env.py:216)
+        self.buf = np.zeros((0, len(self.lo)))
 
     def peek(self, n):
         if len(self.buf) < n:
-            self.buf = np.concatenate([self.buf, self.rs.uniform(-LIMITS[:2], LIMITS[:2], (n - len(self.buf), 2))])
+            self.buf = np.concatenate([self.buf, self.rs.uniform(self.lo, self.hi, (n - len(self.buf), len(self.lo)))])
         return self.buf[:n]
 
     def consume(self, n):
         self.buf = self.buf[n:]
 
 
-def _sample_batch(rngs, need, maps_d, problem_ids, device):
-    """``env.sample_n_points(need[p], need_negative=True)`` (maze_env.py:85-100) for several problems at once: the draws of all
-    problems go through ONE state-check launch per pass; every stream ends exactly where the reference's would."""
+def _sample_batch(rngs, need, maps_d, problem_ids, device, check=None):
+    """``env.sample_n_points(need[p], need_negative=True)`` (maze_env.py:85-100, kuka_env.py:194-209) for several problems at
+    once: the draws of all problems go through ONE state-check launch per pass; every stream ends exactly where the reference's
+    would.  ``check(states_f64_cuda, problem_i32_cuda) -> free u8`` defaults to the 2-D maze check against ``maps_d``."""
+    if check is None:
+        check = lambda st_, pr_: collision.maze_state_fp(st_, maps_d, pr_)  # noqa: E731
     P = len(rngs)
     free = [[] for _ in range(P)]          # per problem: list of [m,2] float64 chunks, concatenated at the end
     coll = [[] for _ in range(P)]
@@ -106,7 +111,7 @@ def _sample_batch(rngs, need, maps_d, problem_ids, device):
         draws = [rngs[p].peek(max(64, int((need[p] - n_got[p]) * 2.5))) for p in todo]
         allp = np.concatenate(draws)
         prob = np.repeat(np.asarray([problem_ids[p] for p in todo], np.int32), [len(d) for d in draws])
-        ok = collision.maze_state_fp(torch.from_numpy(allp).to(device), maps_d, torch.from_numpy(prob).to(device)).cpu().numpy().astype(bool)
+        ok = check(torch.from_numpy(allp).to(device), torch.from_numpy(prob).to(device)).cpu().numpy().astype(bool)
         off, nxt = 0, []
         for p, d in zip(todo, draws):
             f = ok[off:off + len(d)]
@@ -123,7 +128,7 @@ def _sample_batch(rngs, need, maps_d, problem_ids, device):
             if n_got[p] < need[p]:
                 nxt.append(p)
         todo = nxt
-    z = np.zeros((0, 2))
+    z = np.zeros((0, len(rngs[0].lo) if P else 2))
     return [np.concatenate(x) if x else z for x in free], [np.concatenate(x) if x else z for x in coll], counted
 
 
@@ -142,6 +147,73 @@ def _sample_batch_device(seed, streams, next_draw, need, maps_d, problem_ids):
     return free, coll, n_draws.astype(np.int64)
 
 
+class _MazeAdapter:
+    """2-D maze problems (rows of maps / init_states / goal_states)."""
+
+    def __init__(self, maps, init_states, goal_states, problem_ids, seeds, sampler, dev):
+        self.dim, self.dev, self.sampler = 2, dev, sampler
+        self.problem_ids = [int(p) for p in problem_ids]
+        self.seeds = list(seeds)
+        self.maps = np.asarray(maps)
+        self.maps_d = torch.as_tensor(np.ascontiguousarray(self.maps != 0).astype(np.uint8)).to(dev)
+        self.init = np.asarray(init_states, np.float64)[self.problem_ids]
+        self.goal = np.asarray(goal_states, np.float64)[self.problem_ids]
+        self.rngs = [_Stream(s_) for s_ in seeds]
+        self.next_draw = [0] * len(self.problem_ids)
+        self.obs = [(np.argwhere(self.maps[p] == 1) / 15.0 - 0.5).astype(np.float32) for p in self.problem_ids]   # maze_env.py:73-79
+        self.obs_width = 2
+
+    def sample(self, which, n):
+        pids = [self.problem_ids[p] for p in which]
+        if self.sampler == "device":
+            nd = [self.next_draw[p] for p in which]
+            out = _sample_batch_device(0x9E3779B97F4A7C15, [self.seeds[p] for p in which], nd, [n] * len(which), self.maps_d, pids)
+            for i, p in enumerate(which):
+                self.next_draw[p] = nd[i]
+            return out
+        return _sample_batch([self.rngs[p] for p in which], [n] * len(which), self.maps_d, pids, self.dev)
+
+    def search(self, st, v_d, node_ptr_d, n_free_d, ei, edge_ptr_d, logits, goal64, active, n_nodes, n_edges, spec_k, first):
+        slots = torch.tensor(active, dtype=torch.int32, device=self.dev)
+        probs = torch.tensor([self.problem_ids[p] for p in active], dtype=torch.int32, device=self.dev)
+        maze_tree_search(st, v_d, node_ptr_d, n_free_d, ei, edge_ptr_d, logits, goal64, self.maps_d, probs, slots, n_nodes, n_edges,
+                         spec_k=spec_k, first_round=first)
+
+
+class _ArmAdapter:
+    """Arm problems: list of (obstacles [(halfExtents, basePosition), ...], start, goal) as maze_files/kukas_*.pkl stores them."""
+
+    def __init__(self, arm_model, problems, seeds, rrt_eps, dev):
+        self.dev, self.arm_model, self.rrt_eps = dev, int(arm_model), float(rrt_eps)
+        self.dim, lo, hi = collision.arm_model_info(arm_model)
+        self.seeds = list(seeds)
+        self.boxes_d, self.box_ptr_d = collision.pack_boxes([p[0] for p in problems], dev)
+        self.init = np.asarray([np.asarray(p[1], np.float64).reshape(-1) for p in problems])
+        self.goal = np.asarray([np.asarray(p[2], np.float64).reshape(-1) for p in problems])
+        self.rngs = [_Stream(s_, lo, hi) for s_ in seeds]
+        bp = self.box_ptr_d.cpu().numpy()
+        boxes = self.boxes_d.cpu().numpy()
+        self.obs = [boxes[bp[i]:bp[i + 1]].astype(np.float32) for i in range(len(problems))]     # FloatTensor(env.obstacles).view(-1, 6)
+        self.obs_width = 6
+
+    def sample(self, which, n):
+        check = lambda st_, pr_: collision.arm_state_fp(self.arm_model, st_, self.boxes_d, self.box_ptr_d, pr_)  # noqa: E731
+        return _sample_batch([self.rngs[p] for p in which], [n] * len(which), None, list(which), self.dev, check=check)
+
+    def search(self, st, v_d, node_ptr_d, n_free_d, ei, edge_ptr_d, logits, goal64, active, n_nodes, n_edges, spec_k, first):
+        lib = _lib.load()
+        slots = torch.tensor(active, dtype=torch.int32, device=self.dev)
+        B = node_ptr_d.numel() - 1
+        ws = st.workspace(lib.gmp_tree_search_workspace_bytes(B, n_nodes, n_edges), self.dev)
+        _lib.check(lib.gmp_arm_tree_search(
+            self.arm_model, _lib.ptr(v_d), _lib.ptr(node_ptr_d), _lib.ptr(n_free_d), _lib.ptr(ei), ei.stride(0), _lib.ptr(edge_ptr_d),
+            _lib.ptr(logits), _lib.ptr(goal64), _lib.ptr(self.boxes_d), _lib.ptr(self.box_ptr_d), _lib.ptr(slots), self.rrt_eps,
+            _lib.ptr(slots), B, n_nodes, n_edges, int(spec_k), int(bool(first)), _lib.ptr(st.explored), _lib.ptr(st.n_explored),
+            _lib.ptr(st.prev), _lib.ptr(st.elist), _lib.ptr(st.n_elist), _lib.ptr(st.n_checks), _lib.ptr(st.n_spec), _lib.ptr(st.status),
+            _lib.ptr(st.path), _lib.ptr(st.path_len), _lib.ptr(st.path_cost), st.cap_nodes, st.cap_elist, _lib.ptr(ws), ws.numel(),
+            _lib.stream_ptr(self.dev)))
+
+
 @torch.no_grad()
 def explore_batch(model, maps, init_states, goal_states, problem_ids, seeds, batch=100, t_max=100, k=10, loop=5, spec_k=1,
                   device=None, max_checks=20000, sampler="numpy", timings=None):
@@ -153,36 +225,44 @@ def explore_batch(model, maps, init_states, goal_states, problem_ids, seeds, bat
 
     Returns one dict per problem: success, path (float32 waypoints), path_nodes, explored (node ids in tree order), c_explore
     (= env.collision_check_count delta: sampling + edge + goal-region checks), spec_checks (speculative edge checks that were
-    never committed; 0 when spec_k == 1), n_nodes, rounds."""
-    import time as _time
+    never committed; 0 when spec_k == 1), n_nodes, rounds, path_cost."""
     dev = torch.device(device if device is not None else "cuda")
-    P = len(problem_ids)
-    problem_ids = [int(p) for p in problem_ids]
+    ad = _MazeAdapter(maps, init_states, goal_states, problem_ids, seeds, sampler, dev)
+    return _explore_core(ad, model, batch, t_max, k, loop, spec_k, max_checks, timings)
+
+
+@torch.no_grad()
+def explore_batch_arm(model, arm_model, problems, seeds, rrt_eps=0.5, batch=100, t_max=100, k=10, loop=5, spec_k=1, device=None,
+                      max_checks=20000, timings=None):
+    """The same batched planner loop for the arm environments (``collision.ARM_KUKA7`` ...): ``problems[i]`` = (obstacles, start,
+    goal) as the reference's problem files hold them; sampling follows ``KukaEnv.sample_n_points`` on the reference's NumPy
+    stream, the search runs in ``gmp_arm_tree_search`` (``spec_k`` > 1 checks several candidate edges per iteration)."""
+    dev = torch.device(device if device is not None else "cuda")
+    ad = _ArmAdapter(arm_model, problems, seeds, rrt_eps, dev)
+    return _explore_core(ad, model, batch, t_max, k, loop, spec_k, max_checks, timings)
+
+
+def _explore_core(ad, model, batch, t_max, k, loop, spec_k, max_checks, timings):
+    import time as _time
+    dev = ad.dev
+    P = len(ad.seeds)
 
     def _tick(name, t0):
         if timings is not None:                       # phase wall times (synchronised): sample / pack / graph / forward / search
             torch.cuda.synchronize(dev)
             timings[name] = timings.get(name, 0.0) + _time.perf_counter() - t0
         return _time.perf_counter()
-    maps_d = torch.as_tensor(np.ascontiguousarray(np.asarray(maps) != 0).astype(np.uint8)).to(dev)
-    rngs = [_Stream(s) for s in seeds]
-    goal64 = torch.from_numpy(np.ascontiguousarray(np.asarray(goal_states, np.float64)[problem_ids])).to(dev)
+    goal64 = torch.from_numpy(np.ascontiguousarray(ad.goal)).to(dev)
     n_batch = batch
     cap_nodes = 2 * (t_max + 2 * n_batch + 2) + 8
     st = TreeSearchState(P, cap_nodes, 2 + 4 * max_checks, dev)
 
-    next_draw = [0] * P
     t0 = _time.perf_counter()
-    if sampler == "device":
-        new_free, new_coll, counted = _sample_batch_device(0x9E3779B97F4A7C15, list(seeds), next_draw, [n_batch] * P, maps_d, problem_ids)
-    else:
-        new_free, new_coll, counted = _sample_batch(rngs, [n_batch] * P, maps_d, problem_ids, dev)
-    init_np, goal_np = np.asarray(init_states, np.float64), np.asarray(goal_states, np.float64)
-    free = [np.concatenate([init_np[problem_ids[p]][None], goal_np[problem_ids[p]][None], new_free[p]]) for p in range(P)]
+    new_free, new_coll, counted = ad.sample(list(range(P)), n_batch)
+    free = [np.concatenate([ad.init[p][None], ad.goal[p][None], new_free[p]]) for p in range(P)]
     coll = [new_coll[p][:len(new_free[p])] for p in range(P)]                      # collided = collided[:len(free)] BEFORE init/goal join (:180-181)
-    c_sample = counted.copy()
+    c_sample = np.asarray(counted, np.int64).copy()
     t0 = _tick("sample", t0)
-    obs_of = [(np.argwhere(np.asarray(maps[problem_ids[p]]) == 1) / 15.0 - 0.5).astype(np.float32) for p in range(P)]   # maze_env.py:73-79
     active = list(range(P))
     rounds = np.zeros(P, np.int64)
     last_v = [None] * P
@@ -203,18 +283,15 @@ def explore_batch(model, maps, init_states, goal_states, problem_ids, seeds, bat
         et = int(edge_ptr[-1])
         t0 = _tick("graph", t0)
         # ---- model(**data, **obs_data, loop=loop): sparse logits (eval_gnn.py:194)
-        obss = [obs_of[p] for p in active]
+        obss = [ad.obs[p] for p in active]
         obs_ptr = np.concatenate([[0], np.cumsum([len(o) for o in obss])]).astype(np.int32)
-        obs_d = torch.from_numpy(np.concatenate(obss).reshape(-1, 2)).to(dev)
-        goal_d = torch.from_numpy(goal_np[[problem_ids[p] for p in active]].astype(np.float32)).to(dev)
+        obs_d = torch.from_numpy(np.concatenate(obss).reshape(-1, ad.obs_width)).to(dev)
+        goal_d = torch.from_numpy(ad.goal[active].astype(np.float32)).to(dev)
         logits = model.forward_batch(v_d, ei, goal_d, obs_d, node_ptr, edge_ptr, obs_ptr, loop=loop)
         t0 = _tick("forward", t0)
         # ---- the search itself
-        slots = torch.tensor(active, dtype=torch.int32, device=dev)
-        probs = torch.tensor([problem_ids[p] for p in active], dtype=torch.int32, device=dev)
-        maze_tree_search(st, v_d, torch.from_numpy(node_ptr).to(dev), torch.tensor(n_free, dtype=torch.int32, device=dev), ei,
-                         torch.from_numpy(edge_ptr).to(dev), logits, goal64, maps_d, probs, slots, int(node_ptr[-1]), et,
-                         spec_k=spec_k, first_round=first)
+        ad.search(st, v_d, torch.from_numpy(node_ptr).to(dev), torch.tensor(n_free, dtype=torch.int32, device=dev), ei,
+                  torch.from_numpy(edge_ptr).to(dev), logits, goal64, active, int(node_ptr[-1]), et, spec_k, first)
         first = False
         status = st.status.cpu().numpy()
         t0 = _tick("search", t0)
@@ -222,18 +299,11 @@ def explore_batch(model, maps, init_states, goal_states, problem_ids, seeds, bat
         for p in active:
             rounds[p] += 1
             if status[p] == STATUS_CAPACITY:
-                raise _lib.GnnmpError("tree search capacity exceeded for problem %d (raise max_checks)" % problem_ids[p])
+                raise _lib.GnnmpError("tree search capacity exceeded for problem %d (raise max_checks)" % p)
             if status[p] == STATUS_EXHAUSTED and (n_batch + len(free[p]) - 2) <= t_max:      # eval_gnn.py:239-240
                 nxt.append(p)
         if nxt:                                                                               # resample (:242-247)
-            if sampler == "device":
-                nd = [next_draw[p] for p in nxt]
-                nf, nc, cnt = _sample_batch_device(0x9E3779B97F4A7C15, [seeds[p] for p in nxt], nd, [n_batch] * len(nxt), maps_d,
-                                                   [problem_ids[p] for p in nxt])
-                for i, p in enumerate(nxt):
-                    next_draw[p] = nd[i]
-            else:
-                nf, nc, cnt = _sample_batch([rngs[p] for p in nxt], [n_batch] * len(nxt), maps_d, [problem_ids[p] for p in nxt], dev)
+            nf, nc, cnt = ad.sample(nxt, n_batch)
             for i, p in enumerate(nxt):
                 free[p] = np.concatenate([free[p], nf[i]])
                 coll[p] = np.concatenate([coll[p], nc[i]])[:len(free[p])]
@@ -261,4 +331,4 @@ def path_cost(path):
     return float(sum(np.linalg.norm(path[i + 1] - path[i]) for i in range(len(path) - 1)))
 
 
-__all__ = ["TreeSearchState", "maze_tree_search", "explore_batch", "path_cost", "RRT_EPS"]
+__all__ = ["TreeSearchState", "maze_tree_search", "explore_batch", "explore_batch_arm", "path_cost", "RRT_EPS"]

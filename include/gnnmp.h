@@ -178,6 +178,17 @@ int gmp_maze_tree_search(const float* v, const int32_t* node_ptr, const int32_t*
                          int32_t* n_explored_edges, int32_t* n_checks, int32_t* n_spec_checks, int32_t* status,
                          int32_t* path, int32_t* path_len, float* path_cost, int32_t cap_nodes, int32_t cap_explored_edges,
                          void* workspace, int64_t workspace_bytes, void* stream);
+/* The same search for the arm environments (KukaEnv / Kuka2Env / UR5Env / SnakeEnv): env._edge_fp = the arm model's edge check
+ * on float32 states (kuka_env.py:389-411), in_goal_region = float64 distance to goal [S, dof] + one state check
+ * (kuka_env.py:244-249).  Speculation (spec_k > 1) pays here: an edge check is K forward-kinematics passes. */
+int gmp_arm_tree_search(int model, const float* v, const int32_t* node_ptr, const int32_t* n_free, const int64_t* edge_index,
+                        int64_t edge_row_stride, const int32_t* edge_ptr, const float* edge_logits, const double* goal,
+                        const double* boxes, const int32_t* box_ptr, const int32_t* problem_of_graph, double rrt_eps,
+                        const int32_t* slot_of_graph, int64_t n_graphs, int64_t n_nodes_total, int64_t n_edges_total,
+                        int spec_k, int first_round, int32_t* explored, int32_t* n_explored, int32_t* prev,
+                        int32_t* explored_edges, int32_t* n_explored_edges, int32_t* n_checks, int32_t* n_spec_checks,
+                        int32_t* status, int32_t* path, int32_t* path_len, float* path_cost, int32_t cap_nodes,
+                        int32_t cap_explored_edges, void* workspace, int64_t workspace_bytes, void* stream);
 /* The per-problem tuple the reference reduces at the end of eval_gnn (eval_gnn.py:120-134), as rows of 6 floats:
  * (first_problem_id + i, success, path_cost, n_checks, n_spec_checks, n_explored).  These rows are what the multi-GPU run
  * all-gathers (NCCL, host side). */

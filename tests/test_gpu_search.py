@@ -138,3 +138,42 @@ def test_explore_batch_with_device_sampler(cuda_device, setup):
     for r in a:
         if r["success"]:
             assert r["path_nodes"][0] == 0 and r["c_explore"] > 0
+
+
+@pytest.mark.parametrize("tag,model_id,dims,wfile", [("kuka7", 0, (3, 7, 64, 6), "weights_kuka.pt"), ("kuka14", 1, (3, 14, 32, 6), "kuka_14.pt")])
+def test_arm_tree_search_equals_host_loop(cuda_device, tag, model_id, dims, wfile):
+    """gmp_arm_tree_search (the same search kernel instantiated on the arm edge check) against this repo's host mirror of the
+    reference loop on KukaEnv / Kuka2Env problems: explored order, collision_check_count, path -- for spec_k = 1 and 4.  (Arm
+    collision itself is pinned to oracle/arm.c, not to PyBullet.)"""
+    from gnn_motion_planning_b200.environment import Kuka2Env, KukaEnv
+    from gnn_motion_planning_b200.eval_gnn import explore
+    from gnn_motion_planning_b200.model import EncoderProcessDecoder
+    from gnn_motion_planning_b200.search import explore_batch_arm
+    probs = np.load(os.path.join(G, "arm_problems.npz"))
+    boxes, ptr = probs[tag + "_boxes"], probs[tag + "_box_ptr"]
+    problems = []
+    for i in range(6):
+        obs = [(boxes[j, :3], boxes[j, 3:]) for j in range(ptr[i], ptr[i + 1])]
+        problems.append((obs, probs[tag + "_start"][i], probs[tag + "_goal"][i], []))
+    model = EncoderProcessDecoder(*dims).to(cuda_device)
+    model.load_state_dict(torch.load(os.path.join(G, "weights", wfile), map_location="cpu"))
+    seeds = [7000 + i for i in range(len(problems))]
+    kw = dict(batch=60, t_max=180, k=8)
+    res = {sk: explore_batch_arm(model, model_id, [p[:3] for p in problems], seeds, rrt_eps=0.5, spec_k=sk, device=cuda_device, **kw)
+           for sk in (1, 4)}
+    env = (KukaEnv if tag == "kuka7" else Kuka2Env)(problems=problems)
+    n_ok = 0
+    for i, seed in enumerate(seeds):
+        np.random.seed(seed)
+        env.init_new_problem(i)
+        h = explore(env, model, None, smooth=True, smoother="none", **kw)
+        for sk in (1, 4):
+            r = res[sk][i]
+            assert r["success"] == h["success"] and r["n_nodes"] == len(h["data"].v), (tag, i, sk)
+            assert r["explored"] == h["explored"], (tag, i, sk)
+            assert r["c_explore"] == h["c_explore"], (tag, i, sk, r["c_explore"], h["c_explore"])
+            if h["success"]:
+                assert np.allclose(np.array(r["path"]), np.array(h["path"]))
+        n_ok += h["success"]
+    assert res[1][0]["spec_checks"] == 0
+    print("%s: %d / %d solved; uncommitted speculative checks at spec_k=4: %d" % (tag, n_ok, len(seeds), sum(r["spec_checks"] for r in res[4])))

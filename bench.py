@@ -503,6 +503,25 @@ def run_planner(args, rank, local_rank, world):
         torch.cuda.synchronize()
         dt_dev = min(dt_dev, time.perf_counter() - t0) if dt_dev is not None else time.perf_counter() - t0
     search.explore_batch(model, maps, init, goal, ids, seeds, batch=100, t_max=100, k=10, spec_k=1, device=dev, sampler="device", timings=tmd)
+    # the same loop on an arm environment (kuka7, the 48 real problems of tests/golden/arm_problems.npz): the edge check is K
+    # forward-kinematics passes, so checking several candidate edges per iteration (spec_k) pays
+    arm = _arm_problems()
+    bx, bp = arm["kuka7_boxes"], arm["kuka7_box_ptr"]
+    aprobs = [([(bx[j, :3], bx[j, 3:]) for j in range(bp[i], bp[i + 1])], arm["kuka7_start"][i], arm["kuka7_goal"][i]) for i in range(len(bp) - 1)]
+    amodel = EncoderProcessDecoder(workspace_size=3, config_size=7, embed_size=64, obs_size=6).to(dev)
+    amodel.load_state_dict(torch.load(os.path.join(G, "weights", "weights_kuka.pt"), map_location="cpu"))
+    aseeds = [99 + rank * 1000 + i for i in range(len(aprobs))]
+    arm_out = {}
+    for spec_k in (1, 8):
+        search.explore_batch_arm(amodel, 0, aprobs[:8], aseeds[:8], batch=100, t_max=200, k=10, spec_k=spec_k, device=dev)      # warm-up
+        best = None
+        for _rep in range(2):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            ares = search.explore_batch_arm(amodel, 0, aprobs, aseeds, batch=100, t_max=200, k=10, spec_k=spec_k, device=dev)
+            torch.cuda.synchronize()
+            best = min(best, time.perf_counter() - t0) if best is not None else time.perf_counter() - t0
+        arm_out[spec_k] = (best, ares)
     if rank != 0:
         return None
     dt, res = out[1]
@@ -532,6 +551,13 @@ def run_planner(args, rank, local_rank, world):
         "device_sampler": {"value": P / dt_dev, "unit": "problems/s (this rank)", "success": sum(r["success"] for r in res_dev),
                            "phase_wall_ms": {k_: 1e3 * v_ for k_, v_ in tmd.items()},
                            "note": "counter-based Philox sampler on the GPU (gmp_maze_sample_points): a new stream, same semantics"},
+        "kuka7": {"problems": len(aprobs), "config": "explore(batch=100, t_max=200, k=10, smoother='none') on the 48 kuka7 problems of arm_problems.npz",
+                  "value": len(aprobs) / arm_out[1][0], "unit": "problems/s (this rank, spec_k=1)", "success": sum(r["success"] for r in arm_out[1][1]),
+                  "mean_collision_checks": float(np.mean([r["c_explore"] for r in arm_out[1][1]])),
+                  "spec_k8": {"value": len(aprobs) / arm_out[8][0], "unit": "problems/s",
+                              "uncommitted_speculative_checks_per_problem": float(np.mean([r["spec_checks"] for r in arm_out[8][1]])),
+                              "identical_results": all(a["explored"] == b["explored"] and a["c_explore"] == b["c_explore"]
+                                                       for a, b in zip(arm_out[1][1], arm_out[8][1]))}},
         "published_reference": {"value": 11.66, "unit": "problems/s", "source": "main.ipynb raw line 140 (author's machine, unknown hardware; different random mazes)"},
         "timing": "host wall clock around explore_batch (the loop has host code between rounds), best of 3, max over ranks",
         "gpu_launches": 12,

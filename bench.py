@@ -372,7 +372,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sub-records", action="store_true", help="only the headline workload (no C3/C4/C5/planner sub-records)")
     ap.add_argument("--sub-steps", type=int, default=5)
-    ap.add_argument("--ef-mode", default="auto", choices=["auto", "tc", "tc4", "simt"], help="edge-feature kernel variant (A/B profiling)")
+    ap.add_argument("--ef-mode", default="auto", choices=["auto", "tc", "tc4", "tcrd", "simt"], help="edge-feature kernel variant (A/B profiling)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     wl = WORKLOADS[args.workload]

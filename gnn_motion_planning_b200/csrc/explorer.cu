@@ -1388,6 +1388,7 @@ int run_forward(gmp_handle* h, int64_t B, const float* v, const int64_t* edge_in
       {
         GMP_CUDA(cudaFuncSetAttribute(edge_feature_tc_kernel<C, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<C>::kSmemBytes));
         GMP_CUDA(cudaFuncSetAttribute(edge_feature_tc_kernel<C, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<C>::kSmemBytes));
+        GMP_CUDA(cudaFuncSetAttribute(edge_feature_tc_kernel<C, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<C>::kSmemBytes));
       }
     if constexpr (E == 64) {
       GMP_CUDA(cudaFuncSetAttribute(edge_feature64_tc_kernel<C, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tc64Cfg<C>::template smem<0>()));
@@ -1460,8 +1461,16 @@ int run_forward(gmp_handle* h, int64_t B, const float* v, const int64_t* edge_in
       // stages of their own (wider inputs: two more round trips per tile, and the column split does not pay -- measured on
       // kuka14: 11.2 vs 11.8 ms)
       const bool four = m.edge_feature_mode == 2 || (m.edge_feature_mode == -1 && !TcCfg<C>::kSimtIn);
+      bool rd_ok = use_obstacles != 0;     // the ready-driven issuer needs one table load per Block: 1 <= obstacles <= 128 everywhere
+      for (int64_t g = 0; g < B && rd_ok; ++g) {
+        const int no = obs_ptr[g + 1] - obs_ptr[g];
+        if (edge_ptr_h[g + 1] > edge_ptr_h[g] && (no < 1 || no > 128)) rd_ok = false;
+      }
       if (four)                        // round-1 organisation: four warps per tile, thread == row
         edge_feature_tc_kernel<C, 1><<<std::min<int>(tile_e[B], kNumSMs), 384, TcCfg<C>::kSmemBytes, st>>>(
+            W + m.w.tc_img, v, ws.csr_src, ws.csr_dst, ws.tc_unit_meta, tile_e[B], ws.tc_tables, tc_stride, use_obstacles, ws.P, ws.Q);
+      else if (rd_ok && (m.edge_feature_mode == 3 || getenv("GMP_TC_RD")))   // eight warps per tile + ready-driven issuer
+        edge_feature_tc_kernel<C, 2, true><<<std::min<int>(tile_e[B], kNumSMs), 544, TcCfg<C>::kSmemBytes, st>>>(
             W + m.w.tc_img, v, ws.csr_src, ws.csr_dst, ws.tc_unit_meta, tile_e[B], ws.tc_tables, tc_stride, use_obstacles, ws.P, ws.Q);
       else                             // eight warps per tile, columns split between warp pairs
         edge_feature_tc_kernel<C, 2><<<std::min<int>(tile_e[B], kNumSMs), 544, TcCfg<C>::kSmemBytes, st>>>(
@@ -1611,7 +1620,7 @@ extern "C" int gmp_explorer_bad_edges(gmp_handle* h, void* stream) {
 
 extern "C" int gmp_explorer_set_edge_feature_mode(gmp_handle* h, int mode) {
   GMP_REQUIRE(h, "null handle");
-  GMP_REQUIRE(mode >= -1 && mode <= 2, "mode: -1 auto, 0 fp32 SIMT, 1 tcgen05 3xTF32, 2 tcgen05 with the round-1 four-warp tiles");
+  GMP_REQUIRE(mode >= -1 && mode <= 3, "mode: -1 auto, 0 fp32 SIMT, 1 tcgen05 3xTF32, 2 tcgen05 with the round-1 four-warp tiles, 3 tcgen05 with the ready-driven issuer");
   h->ex.edge_feature_mode = mode;
   return GMP_OK;
 }

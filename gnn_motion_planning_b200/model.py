@@ -195,7 +195,7 @@ class EncoderProcessDecoder:
         epilogue warps per 128-edge tile, columns split between warp pairs) or "tc4" (embed 32 only: the round-1 organisation,
         four warps per tile).  All meet the 1e-4 logit tolerance; the switch exists for A/B parity tests and profiling."""
         self._ensure_uploaded()
-        code = {"auto": -1, "simt": 0, "tc": 1, "tc4": 2}[mode]
+        code = {"auto": -1, "simt": 0, "tc": 1, "tc4": 2, "tcrd": 3}[mode]
         _lib.check(_lib.load().gmp_explorer_set_edge_feature_mode(self._handle, code))
 
     def last_bad_edges(self):

@@ -1460,21 +1460,28 @@ int run_forward(gmp_handle* h, int64_t B, const float* v, const int64_t* edge_in
       // auto: eight warps per tile where the first encoder layers are plain FMAs (2c <= 8: maze); four where they are MMA
       // stages of their own (wider inputs: two more round trips per tile, and the column split does not pay -- measured on
       // kuka14: 11.2 vs 11.8 ms)
-      const bool four = m.edge_feature_mode == 2 || (m.edge_feature_mode == -1 && !TcCfg<C>::kSimtIn);
-      bool rd_ok = use_obstacles != 0;     // the ready-driven issuer needs one table load per Block: 1 <= obstacles <= 128 everywhere
+      const int mode = m.edge_feature_mode;
+      const bool four = mode == 2 || ((mode == -1 || mode == 3) && !TcCfg<C>::kSimtIn);
+      // one issuer warp per tile (RD) needs exactly one table load per Block: 1 <= obstacles <= 128 in every graph with edges
+      bool rd_ok = use_obstacles != 0;
       for (int64_t g = 0; g < B && rd_ok; ++g) {
         const int no = obs_ptr[g + 1] - obs_ptr[g];
         if (edge_ptr_h[g + 1] > edge_ptr_h[g] && (no < 1 || no > 128)) rd_ok = false;
       }
-      if (four)                        // round-1 organisation: four warps per tile, thread == row
-        edge_feature_tc_kernel<C, 1><<<std::min<int>(tile_e[B], kNumSMs), 384, TcCfg<C>::kSmemBytes, st>>>(
-            W + m.w.tc_img, v, ws.csr_src, ws.csr_dst, ws.tc_unit_meta, tile_e[B], ws.tc_tables, tc_stride, use_obstacles, ws.P, ws.Q);
-      else if (rd_ok && (m.edge_feature_mode == 3 || getenv("GMP_TC_RD")))   // eight warps per tile + ready-driven issuer
-        edge_feature_tc_kernel<C, 2, true><<<std::min<int>(tile_e[B], kNumSMs), 544, TcCfg<C>::kSmemBytes, st>>>(
-            W + m.w.tc_img, v, ws.csr_src, ws.csr_dst, ws.tc_unit_meta, tile_e[B], ws.tc_tables, tc_stride, use_obstacles, ws.P, ws.Q);
-      else                             // eight warps per tile, columns split between warp pairs
-        edge_feature_tc_kernel<C, 2><<<std::min<int>(tile_e[B], kNumSMs), 544, TcCfg<C>::kSmemBytes, st>>>(
-            W + m.w.tc_img, v, ws.csr_src, ws.csr_dst, ws.tc_unit_meta, tile_e[B], ws.tc_tables, tc_stride, use_obstacles, ws.P, ws.Q);
+      // ... and is used with the eight-warps organisation only: with four warps per tile (wide inputs) it measured 19.1 ms
+      // against 10.9 ms lockstep on C4 (profiles/r2_rd_issuer.md)
+      const char* rd_env = getenv("GMP_TC_RD");                       // A/B switch: "0" lockstep issuer, anything else per-tile issuers
+      const bool rd = rd_ok && !four && (rd_env ? rd_env[0] != '0' : (mode == 3 || mode == -1));
+      const int grid = std::min<int>(tile_e[B], kNumSMs);
+#define GMP_EF_LAUNCH(HALVES, RD, THREADS)                                                                                   \
+  edge_feature_tc_kernel<C, HALVES, RD><<<grid, THREADS, TcCfg<C>::kSmemBytes, st>>>(                                       \
+      W + m.w.tc_img, v, ws.csr_src, ws.csr_dst, ws.tc_unit_meta, tile_e[B], ws.tc_tables, tc_stride, use_obstacles, ws.P, ws.Q)
+      if (four) {                      // four warps per tile, thread == row
+        GMP_EF_LAUNCH(1, false, 384);
+      } else {                         // eight warps per tile, columns split between warp pairs
+        if (rd) GMP_EF_LAUNCH(2, true, 576); else GMP_EF_LAUNCH(2, false, 544);
+      }
+#undef GMP_EF_LAUNCH
       GMP_LAUNCH_CHECK();
       tc_done = true;
     }

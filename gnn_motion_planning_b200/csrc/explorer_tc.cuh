@@ -160,13 +160,16 @@ __device__ __forceinline__ void layernorm_row(float* x, const float* __restrict_
 //             under a 64-thread named barrier.  The softmax is rolled over 16-column pieces in two passes (maximum, then
 //             exponentials) -- no 96-entry register array -- so a thread fits in 120 registers and FOUR epilogue warps share
 //             each scheduler instead of two (round 1: issue slots 35 % busy, epilogues 81 % of a tile's time).  544 threads.
-// RD = true: READY-DRIVEN issuer (requires 1 <= obstacles <= 128 in every graph and use_obstacles): each tile has its own
-//             program counter over the unit's stage list and the issuer serves whichever tile has published its operands -- whole
-//             MMA groups, never interleaved -- instead of stage-by-stage in the fixed order tile 0, tile 1.  The only coupling left
-//             between the tiles is the single obstacle-table buffer: table k+1 is loaded once BOTH tiles have issued map_feed.w_1
-//             of table k's Block, and a tile may start a Block only when its table has landed.
+// RD = true: ONE ISSUER WARP PER TILE (requires 1 <= obstacles <= 128 in every graph and use_obstacles; 576 threads).  Each issuer
+//             sleeps on its own tile's `ready` barrier and issues that tile's MMA groups only, so the two tiles are no longer
+//             served stage by stage in the fixed order tile 0, tile 1 and drift apart instead of contending for the same
+//             issue slots and the same tensor pipe at the same moments.  The only coupling left is the single obstacle-table
+//             buffer: the second issuer to pass map_feed.w_1 of a Block loads the next table, and both wait for it to land
+//             before they issue the next Block.  (A first version -- one warp polling both `ready` barriers and serving
+//             whichever tile had published -- was bit-identical but slower than lockstep: every instruction of the poll loop
+//             costs ~5 cycles next to four epilogue warps on the same scheduler, profiles/r2_rd_issuer.md.)
 template <int C, int HALVES, bool RD = false>
-__global__ void __launch_bounds__(HALVES == 1 ? 384 : 544, 1) edge_feature_tc_kernel(
+__global__ void __launch_bounds__(HALVES == 1 ? 384 : (RD ? 576 : 544), 1) edge_feature_tc_kernel(
     const float* __restrict__ tcw, const float* __restrict__ v, const int32_t* __restrict__ csr_src,
     const int32_t* __restrict__ csr_dst, const int4* __restrict__ unit_meta, int n_units, const float* __restrict__ tc_tables,
     int64_t tc_tab_stride, int use_obstacles, float* __restrict__ P, float* __restrict__ Q) {
@@ -177,6 +180,7 @@ __global__ void __launch_bounds__(HALVES == 1 ? 384 : 544, 1) edge_feature_tc_ke
   float* tabbuf = smem_tc + Cf::kImage;
   __shared__ uint64_t bar_ready[2], bar_done[2], bar_tabfull;
   __shared__ uint32_t tmem_slot;
+  __shared__ int tab_released;                                                 // RD: issuers that are done with the current table
   __shared__ float xch[HALVES == 2 ? 2 * 2 * 2 * 128 : 1];                    // [tile][parity][half][row]: row-reduction exchange
   constexpr int kIssuer = 8 * HALVES;                                          // warp index of the MMA issuer
 
@@ -188,6 +192,7 @@ __global__ void __launch_bounds__(HALVES == 1 ? 384 : 544, 1) edge_feature_tc_ke
     for (int i = threadIdx.x; i < Cf::kImage / 4; i += blockDim.x) d4[i] = __ldg(s4 + i);
   }
   if (threadIdx.x == 0) {
+    tab_released = 0;
     mbar_init(&bar_ready[0], 128 * HALVES); mbar_init(&bar_ready[1], 128 * HALVES);
     mbar_init(&bar_done[0], 1); mbar_init(&bar_done[1], 1);
     mbar_init(&bar_tabfull, 1);
@@ -208,148 +213,113 @@ __global__ void __launch_bounds__(HALVES == 1 ? 384 : 544, 1) edge_feature_tc_ke
       asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
     }
   }
-  if (warp_u > kIssuer) {
-    // warps 9-11 only pad the issuer's warpgroup (HALVES == 1)
-  } else if (RD && warp_u == kIssuer) {
-    // =================================================================== ready-driven MMA issuer / table loader
+  if (RD && (warp_u == kIssuer || warp_u == kIssuer + 1)) {
+    // =================================================================== one MMA issuer warp PER TILE (RD)
     if constexpr (RD) {
+      const int t = warp_u - kIssuer;
       const uint32_t tm_u = __shfl_sync(0xffffffffu, tm, 0);
       const uint32_t img_s = smem_u32(img), tab_s = smem_u32(tabbuf);
-      auto load_meta = [&](int u) {
-        int4 mm = make_int4(0, 0, 0, 0);
-        if (u < n_units) mm = __ldg(unit_meta + u);
-        mm.z = __shfl_sync(0xffffffffu, mm.z, 0);
-        mm.w = __shfl_sync(0xffffffffu, mm.w, 0);
-        return mm;
-      };
+      const uint32_t tc = tm_u + (uint32_t)t * 256u, xh = tc + Cf::cXH, xl = tc + Cf::cXL;
       auto wd = [&](int off, int rows) { return umma::desc_lo32(img_s + (uint32_t)off * 4u, (uint32_t)rows); };
-      auto test_ready = [&](int t, uint32_t phase) -> bool {      // non-blocking; result made provably warp-uniform
-        uint32_t done;
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(smem_u32(&bar_ready[t])), "r"(phase) : "memory");
-        return __shfl_sync(0xffffffffu, done, 0) != 0;
-      };
-      constexpr int kPre = Cf::kSimtIn ? 1 : 2;                   // stages before the Blocks: [edge_free_code.0] edge_free_code.2
-      constexpr int kPost = Cf::kSimtIn ? 1 : 2;                  // stages after them: [edge_code.0] tail
-      int unit_t[2] = {(int)blockIdx.x, (int)blockIdx.x}, pc[2] = {0, 0}, w1_done[2] = {0, 0};
-      uint32_t rph[2] = {0, 0}, full_ph = 0;
-      int4 meta_t[2];
-      meta_t[0] = meta_t[1] = load_meta(blockIdx.x);
-      int tab_loaded = -1, tab_landed = -1;                       // table k = 3 * (local unit index) + Block
-      auto try_load = [&]() {                                      // table tab_loaded + 1, once both tiles are done with its predecessor
-        const int k = tab_loaded + 1;
-        if (min(w1_done[0], w1_done[1]) < k) return;
-        const int u = (int)blockIdx.x + (k / 3) * (int)gridDim.x;
-        if (u >= n_units) return;
-        const int4 mm = load_meta(u);
-        const int nch = tc_nchunks(mm.z), per = tc_per(mm.z, nch);
-        const float* src = tc_tables + (size_t)(k % 3) * tc_tab_stride + (size_t)mm.w;
+      auto raw_meta = [&](int u) { return u < n_units ? __ldg(unit_meta + u) : make_int4(0, 0, 0, 0); };
+      auto load_table = [&](const int4 mm_raw, int blk) {          // table of (unit with metadata mm_raw, Block blk) -> tabbuf
+        const int O = __shfl_sync(0xffffffffu, mm_raw.z, 0), off = __shfl_sync(0xffffffffu, mm_raw.w, 0);
+        const int nch = tc_nchunks(O), per = tc_per(O, nch);
+        const float* src = tc_tables + (size_t)blk * tc_tab_stride + (size_t)off;
         const uint32_t bytes = (uint32_t)(nch * 4 * E * per) * 4u;
         if (umma::elect_one()) {
           mbar_expect_tx(&bar_tabfull, bytes);
           tma_bulk_g2s(tabbuf, src, bytes, &bar_tabfull);
         }
         __syncwarp();
-        tab_loaded = k;
       };
-      try_load();
-      int first = 0;
+      uint32_t rph = 0, full_ph = 0;
+      int4 meta_cur = raw_meta(blockIdx.x), meta_next = raw_meta(blockIdx.x + gridDim.x);   // one unit ahead of its use
+      if (t == 0 && (int)blockIdx.x < n_units) load_table(meta_cur, 0);
 #ifdef GMP_TC_PROFILE
-      long long rd_issue[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, rd_idle = 0, rd_t0 = clock64(), rd_last = rd_t0;
-      int rd_cnt[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+      long long prof_ready = 0, prof_tab = 0, prof_issue = 0, prof_t0 = clock64();
+#define GMP_RD_T(VAR, ...) { const long long c0 = clock64(); __VA_ARGS__; VAR += clock64() - c0; }
+#else
+#define GMP_RD_T(VAR, ...) { __VA_ARGS__; }
 #endif
-      while (unit_t[0] < n_units || unit_t[1] < n_units) {
-#pragma unroll
-        for (int tt = 0; tt < 2; ++tt) {
-          const int t = tt ^ first;
-          if (unit_t[t] >= n_units) continue;
-          const int O = meta_t[t].z;
-          const int nch = tc_nchunks(O), per = tc_per(O, nch);
-          const int per_blk = 4 + (nch == 2 ? 1 : 0);
-          const int n_stages = kPre + 3 * per_blk + kPost;
-          // decode the stage: kind 0 enc0, 1 ef2, 2 GV+scores, 3 PV0, 4 PV1, 5 w1, 6 w2, 7 ec0, 8 tail
-          int s = pc[t], kind, blk = 0;
-          if (s < kPre) kind = (!Cf::kSimtIn && s == 0) ? 0 : 1;
-          else if (s < kPre + 3 * per_blk) {
-            s -= kPre;
-            blk = s / per_blk;
-            const int r = s - blk * per_blk;
-            kind = r == 0 ? 2 : (r == 1 ? 3 : (r == per_blk - 2 ? 5 : (r == per_blk - 1 ? 6 : 4)));
-          } else kind = (!Cf::kSimtIn && s == kPre + 3 * per_blk) ? 7 : 8;
-          const int k_tab = 3 * ((unit_t[t] - (int)blockIdx.x) / (int)gridDim.x) + blk;
-          if (kind == 2 && tab_loaded < k_tab) {                  // this Block's table is not even requested yet
-            try_load();
-            if (tab_loaded < k_tab) continue;
-          }
-          if (kind == 2 && tab_landed < k_tab) {                  // requested but not landed yet: do not block -- the other tile may be ready
-            uint32_t landed;
-            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                         : "=r"(landed) : "r"(smem_u32(&bar_tabfull)), "r"(full_ph) : "memory");
-            if (__shfl_sync(0xffffffffu, landed, 0) == 0) continue;
-            full_ph ^= 1u;
-            tab_landed = k_tab;
-          }
-          if (!test_ready(t, rph[t])) continue;
-          rph[t] ^= 1u;
-          umma::fence_after_sync();
-#ifdef GMP_TC_PROFILE
-          const long long i0 = clock64();
-          rd_idle += i0 - rd_last;
-#endif
-          if (umma::elect_one()) {
-            const uint32_t tc = tm_u + (uint32_t)t * 256u;
-            const uint32_t xh = tc + Cf::cXH, xl = tc + Cf::cXL;
-            const int wb = Cf::BLK + blk * Cf::kBlk;
-            const uint32_t sub = (uint32_t)(4 * E * per) * 4u, pl = (uint32_t)(E * per) * 4u;
-            if (kind == 0) umma::gemm3_fixed<E, K0, 64>(tc + Cf::cA1, xh, xl, wd(Cf::ENC0, 64), wd(Cf::ENC0 + 64 * K0, 64), false);
-            else if (kind == 1) umma::gemm3_fixed<E, E, E>(tc + Cf::cA1, xh, xl, wd(Cf::EF2, E), wd(Cf::EF2 + E * E, E), false);
-            else if (kind == 2) {
-              umma::gemm3_fixed<64, E, 64>(tc + Cf::cA1, xh, xl, wd(wb, 64), wd(wb + 64 * E, 64), false);
-              umma::gemm3_n<E>(tc + Cf::cSC, xh, xl, umma::desc_lo32(tab_s, (uint32_t)per), umma::desc_lo32(tab_s + pl, (uint32_t)per), per);
-              if (nch == 2)
-                umma::gemm3_n<E>(tc + Cf::cSC1, xh, xl, umma::desc_lo32(tab_s + sub, (uint32_t)per), umma::desc_lo32(tab_s + sub + pl, (uint32_t)per), per);
-            } else if (kind == 3)
-              umma::gemm3_k<E, E>(tc + (nch == 2 ? Cf::cPV2 : Cf::cPV1), tc + Cf::cSC, tc + Cf::cPL, umma::desc_lo32(tab_s + 2 * pl, E),
-                                  umma::desc_lo32(tab_s + 3 * pl, E), per);
-            else if (kind == 4)
-              umma::gemm3_k<E, E>(tc + Cf::cPV2, tc + Cf::cSC1, tc + Cf::cPL, umma::desc_lo32(tab_s + sub + 2 * pl, E),
-                                  umma::desc_lo32(tab_s + sub + 3 * pl, E), per);
-            else if (kind == 5) umma::gemm3_fixed<E, E, E>(tc + Cf::cA1, xh, xl, wd(wb + Cf::oW1, E), wd(wb + Cf::oW1 + E * E, E), false);
-            else if (kind == 6) umma::gemm3_fixed<E, E, E>(tc + Cf::cA1, xh, xl, wd(wb + Cf::oW2, E), wd(wb + Cf::oW2 + E * E, E), false);
-            else if (kind == 7)
-              umma::gemm3_fixed<E, K0, 64>(tc + Cf::cSC, tc + Cf::cHH, tc + Cf::cHL, wd(Cf::ENC0, 64) + E, wd(Cf::ENC0 + 64 * K0, 64) + E, false);
-            else {
-              umma::gemm3_fixed<64, E, 64>(tc + Cf::cA1, xh, xl, wd(Cf::QP, 64), wd(Cf::QP + 64 * E, 64), false);
-              umma::gemm3_fixed<E, E, E>(tc + Cf::cA1 + 32, tc + Cf::cHH, tc + Cf::cHL, wd(Cf::W52, E), wd(Cf::W52 + E * E, E), true);
-            }
-            umma::commit(&bar_done[t]);
-          }
-          __syncwarp();
-#ifdef GMP_TC_PROFILE
-          rd_last = clock64();
-          rd_issue[kind] += rd_last - i0;
-          rd_cnt[kind] += 1;
-#endif
-          if (kind == 5) {                                         // this tile's P.V products of the Block have retired
-            w1_done[t] += 1;
-            try_load();
-          }
-          if (++pc[t] == n_stages) {
-            pc[t] = 0;
-            unit_t[t] += (int)gridDim.x;
-            meta_t[t] = load_meta(unit_t[t]);
-          }
-          first = t ^ 1;                                           // fairness: look at the other tile first next time
+      // one stage of THIS tile: wait for its operands, issue, commit (exactly one commit per `ready` phase)
+#define GMP_RD_STAGE(...)                                                        \
+  {                                                                              \
+    GMP_RD_T(prof_ready, umma::mbar_wait_guard(&bar_ready[t], rph));             \
+    rph ^= 1u;                                                                   \
+    umma::fence_after_sync();                                                    \
+    GMP_RD_T(prof_issue,                                                         \
+      if (umma::elect_one()) {                                                   \
+        __VA_ARGS__;                                                             \
+        umma::commit(&bar_done[t]);                                              \
+      }                                                                          \
+      __syncwarp());                                                             \
+  }
+      for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        const int O = __shfl_sync(0xffffffffu, meta_cur.z, 0);
+        const int nch = tc_nchunks(O), per = tc_per(O, nch);
+        const uint32_t sub = (uint32_t)(4 * E * per) * 4u, pl = (uint32_t)(E * per) * 4u;   // bytes per sub-chunk / per plane
+        const uint32_t mt_h0 = umma::desc_lo32(tab_s, (uint32_t)per), mt_l0 = umma::desc_lo32(tab_s + pl, (uint32_t)per),
+                       vt_h0 = umma::desc_lo32(tab_s + 2 * pl, E), vt_l0 = umma::desc_lo32(tab_s + 3 * pl, E);
+        const uint32_t mt_h1 = umma::desc_lo32(tab_s + sub, (uint32_t)per), mt_l1 = umma::desc_lo32(tab_s + sub + pl, (uint32_t)per),
+                       vt_h1 = umma::desc_lo32(tab_s + sub + 2 * pl, E), vt_l1 = umma::desc_lo32(tab_s + sub + 3 * pl, E);
+        if constexpr (!Cf::kSimtIn) {
+          GMP_RD_STAGE(umma::gemm3_fixed<E, K0, 64>(tc + Cf::cA1, xh, xl, wd(Cf::ENC0, 64), wd(Cf::ENC0 + 64 * K0, 64), false));
         }
+        GMP_RD_STAGE(umma::gemm3_fixed<E, E, E>(tc + Cf::cA1, xh, xl, wd(Cf::EF2, E), wd(Cf::EF2 + E * E, E), false));
+        for (int blk = 0; blk < 3; ++blk) {
+          const int wb = Cf::BLK + blk * Cf::kBlk;
+          const uint32_t gv_h = wd(wb, 64), gv_l = wd(wb + 64 * E, 64);
+          GMP_RD_T(prof_tab, umma::mbar_wait_guard(&bar_tabfull, full_ph));   // this Block's table has landed (both issuers watch it)
+          full_ph ^= 1u;
+          GMP_RD_STAGE({
+            umma::gemm3_fixed<64, E, 64>(tc + Cf::cA1, xh, xl, gv_h, gv_l, false);
+            umma::gemm3_n<E>(tc + Cf::cSC, xh, xl, mt_h0, mt_l0, per);
+            if (nch == 2) umma::gemm3_n<E>(tc + Cf::cSC1, xh, xl, mt_h1, mt_l1, per);
+          });
+          GMP_RD_STAGE(umma::gemm3_k<E, E>(tc + (nch == 2 ? Cf::cPV2 : Cf::cPV1), tc + Cf::cSC, tc + Cf::cPL, vt_h0, vt_l0, per));
+          if (nch == 2) {
+            GMP_RD_STAGE(umma::gemm3_k<E, E>(tc + Cf::cPV2, tc + Cf::cSC1, tc + Cf::cPL, vt_h1, vt_l1, per));
+          }
+          GMP_RD_STAGE(umma::gemm3_fixed<E, E, E>(tc + Cf::cA1, xh, xl, wd(wb + Cf::oW1, E), wd(wb + Cf::oW1 + E * E, E), false));
+          // this tile has published map_feed.w_1's operand, so its P.V products of the Block have retired.  The SECOND issuer to
+          // get here refills the table buffer (next Block / next unit) behind the FFN stages; nobody blocks
+          {
+            int prev = 0;
+            if ((threadIdx.x & 31) == 0) {
+              __threadfence_block();
+              prev = atomicAdd(&tab_released, 1);
+              __threadfence_block();
+            }
+            prev = __shfl_sync(0xffffffffu, prev, 0);
+            if (prev & 1) {
+              if (blk < 2) load_table(meta_cur, blk + 1);
+              else if (unit + (int)gridDim.x < n_units) load_table(meta_next, 0);
+            }
+          }
+          GMP_RD_STAGE(umma::gemm3_fixed<E, E, E>(tc + Cf::cA1, xh, xl, wd(wb + Cf::oW2, E), wd(wb + Cf::oW2 + E * E, E), false));
+        }
+        if constexpr (!Cf::kSimtIn) {
+          GMP_RD_STAGE(umma::gemm3_fixed<E, K0, 64>(tc + Cf::cSC, tc + Cf::cHH, tc + Cf::cHL, wd(Cf::ENC0, 64) + E,
+                                                    wd(Cf::ENC0 + 64 * K0, 64) + E, false));
+        }
+        GMP_RD_STAGE({
+          umma::gemm3_fixed<64, E, 64>(tc + Cf::cA1, xh, xl, wd(Cf::QP, 64), wd(Cf::QP + 64 * E, 64), false);
+          umma::gemm3_fixed<E, E, E>(tc + Cf::cA1 + 32, tc + Cf::cHH, tc + Cf::cHL, wd(Cf::W52, E), wd(Cf::W52 + E * E, E), true);
+        });
+        meta_cur = meta_next;
+        meta_next = raw_meta(unit + 2 * (int)gridDim.x);
       }
+#undef GMP_RD_STAGE
+#undef GMP_RD_T
 #ifdef GMP_TC_PROFILE
       if (blockIdx.x == 0 && (threadIdx.x & 31) == 0)
-        printf("tc rd issuer: total %lld cyc, polling %lld; issue cycles (count) per kind: enc0 %lld(%d) ef2 %lld(%d) GV %lld(%d) PV0 %lld(%d) PV1 %lld(%d) "
-               "w1 %lld(%d) w2 %lld(%d) ec0 %lld(%d) tail %lld(%d)\n", clock64() - rd_t0, rd_idle, rd_issue[0], rd_cnt[0], rd_issue[1], rd_cnt[1],
-               rd_issue[2], rd_cnt[2], rd_issue[3], rd_cnt[3], rd_issue[4], rd_cnt[4], rd_issue[5], rd_cnt[5], rd_issue[6], rd_cnt[6], rd_issue[7],
-               rd_cnt[7], rd_issue[8], rd_cnt[8]);
+        printf("tc rd issuer %d: total %lld cyc; waiting ready %lld tables %lld; issuing %lld\n", t, clock64() - prof_t0, prof_ready, prof_tab,
+               prof_issue);
 #endif
     }
+  } else if (warp_u > kIssuer) {
+    // warps 9-11 only pad the issuer's warpgroup (HALVES == 1)
   } else if (warp_u == kIssuer) {
     // =================================================================== MMA issuer / table loader
     const uint32_t tm_u = __shfl_sync(0xffffffffu, tm, 0);

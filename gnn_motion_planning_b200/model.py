@@ -191,9 +191,11 @@ class EncoderProcessDecoder:
     PHASES = ("csr_build", "goal_index", "obstacle_stream", "node_pre", "edge_feature", "node_loop", "edge_msg", "policy")
 
     def set_edge_feature_mode(self, mode):
-        """Arithmetic of the edge-feature stage: "auto" (tcgen05 3xTF32 tensor cores), "simt" (fp32 FMA), "tc" (= auto: eight
-        epilogue warps per 128-edge tile, columns split between warp pairs) or "tc4" (embed 32 only: the round-1 organisation,
-        four warps per tile).  All meet the 1e-4 logit tolerance; the switch exists for A/B parity tests and profiling."""
+        """Arithmetic of the edge-feature stage: "auto" (tcgen05 3xTF32 tensor cores), "simt" (fp32 FMA), "tc" (eight epilogue
+        warps per 128-edge tile, columns split between warp pairs, ONE lockstep MMA issuer), "tc4" (embed 32 only: the round-1
+        organisation, four warps per tile) or "tcrd" (= what auto picks for narrow inputs when every graph has 1..128 obstacles:
+        eight warps per tile and one issuer warp PER TILE).  All meet the 1e-4 logit tolerance and "tc" / "tcrd" are bit-identical;
+        the switch exists for A/B parity tests and profiling."""
         self._ensure_uploaded()
         code = {"auto": -1, "simt": 0, "tc": 1, "tc4": 2, "tcrd": 3}[mode]
         _lib.check(_lib.load().gmp_explorer_set_edge_feature_mode(self._handle, code))

@@ -213,21 +213,23 @@ def test_forward_is_stable_under_concurrent_streams(cuda_device):
     torch.cuda.synchronize()
 
 
-def test_ready_driven_issuer_is_bit_identical(cuda_device):
-    """mode "tcrd": the edge-feature kernel with the ready-driven MMA issuer (per-tile program counters, tiles served in the order
-    they publish) computes exactly what the lockstep issuer computes -- same MMAs, same epilogues, another interleaving -- on ragged
-    batches with 1..128 obstacles per graph (one table load per Block: 57, 96, 97, 128 cover lone chunks and pairs), repeatedly
-    and under a concurrent stream."""
+@pytest.mark.parametrize("wfile,dims,lockstep", [("weights_maze.pt", (2, 2, 32, 2), "tc"), ("weights_maze_3.pt", (2, 3, 32, 2), "tc")])
+def test_ready_driven_issuer_is_bit_identical(cuda_device, wfile, dims, lockstep):
+    """mode "tcrd" (what auto picks when every graph has 1..128 obstacles): the edge-feature kernel with ONE ISSUER WARP PER TILE
+    computes exactly what the lockstep issuer (modes "tc" / "tc4": tile 0 then tile 1, stage by stage) computes -- same MMAs, same
+    epilogues, another interleaving -- on ragged batches (57, 96, 97, 128 obstacles cover lone table chunks and pairs), repeatedly
+    and under a concurrent stream.  (Eight-warps-per-tile organisation only: wide-input models keep the lockstep issuer.)"""
     from gnn_motion_planning_b200 import graph
     from oracle import knn_graph as o_knn
-    m = make_model("weights_maze.pt", (2, 2, 32, 2), cuda_device)
+    m = make_model(wfile, dims, cuda_device)
+    c, s_obs = dims[1], dims[3]
     rng = np.random.default_rng(21)
     vs, eis, obs = [], [], []
     for (n, k), o in zip([(700, 14), (300, 12), (513, 9), (129, 20), (900, 10), (64, 6)], [57, 96, 97, 128, 1, 70]):
-        v = rng.uniform(-1, 1, (n, 2)).astype(np.float32)
+        v = rng.uniform(-1, 1, (n, c)).astype(np.float32)
         vs.append(v)
         eis.append(o_knn.knn_graph_edges(v, n, k))
-        obs.append(rng.uniform(-0.5, 0.5, (o, 2)).astype(np.float32))
+        obs.append(rng.uniform(-0.5, 0.5, (o, s_obs)).astype(np.float32))
     node_ptr = np.cumsum([0] + [len(v) for v in vs])
     edge_ptr = np.cumsum([0] + [e.shape[1] for e in eis])
     obs_ptr = np.cumsum([0] + [len(o) for o in obs])
@@ -235,7 +237,7 @@ def test_ready_driven_issuer_is_bit_identical(cuda_device):
     EI = torch.from_numpy(np.concatenate(eis, 1)).to(cuda_device)
     GOAL = torch.from_numpy(np.stack([v[1] for v in vs])).to(cuda_device)
     OBS = torch.from_numpy(np.concatenate(obs)).to(cuda_device)
-    m.set_edge_feature_mode("tc")
+    m.set_edge_feature_mode(lockstep)
     want = m.forward_batch(V, EI, GOAL, OBS, node_ptr, edge_ptr, obs_ptr, loop=5).clone()
     m.set_edge_feature_mode("tcrd")
     side = torch.cuda.Stream(device=cuda_device)

@@ -791,9 +791,12 @@ def run_single(args, wl, rank, local_rank, world):
         # tcgen05 path: 3xTF32 (three kind::tf32 MMAs per product, fp32 accumulate in TMEM).  TF32 dense runs at half the bf16
         # rate and every product is issued three times, so the ceiling of this arithmetic is peak/6 of the bf16 figure.
         halves = 1 if (args.ef_mode == "tc4" or (args.ef_mode == "auto" and 2 * c > 8)) else 2     # explorer.cu: auto mode
-        ef_kernel = "edge_feature_tc_kernel<%d,%d>" % (c, halves)
+        # explorer.cu: one MMA issuer warp per tile (third template argument) for the eight-warp organisation when every graph
+        # has 1..128 obstacles (true of every bench workload) unless GMP_TC_RD=0 / an explicit lockstep mode
+        rd = halves == 2 and args.ef_mode in ("auto", "tcrd") and os.environ.get("GMP_TC_RD", "1")[0] != "0"
+        ef_kernel = "edge_feature_tc_kernel<%d,%d%s>" % (c, halves, ",true" if rd else "")
         ef_note = ("tcgen05.mma kind::tf32, 3xTF32 split operands (1e-4 logit tolerance rules out 1-pass TF32/BF16), A operands and "
-                   "accumulators in TMEM; second template argument = epilogue warp groups per 128-edge tile (2: eight warps, columns split); against the 3xTF32 ceiling (bf16 peak / 6 = %.0f TFLOP/s) the fraction is %.3f; the fp32 SIMT "
+                   "accumulators in TMEM; second template argument = epilogue warp groups per 128-edge tile (2: eight warps, columns split), third = one MMA issuer warp per tile; against the 3xTF32 ceiling (bf16 peak / 6 = %.0f TFLOP/s) the fraction is %.3f; the fp32 SIMT "
                    "kernel it replaces peaked at 148 SM x 128 FMA x %.0f MHz = %.1f TFLOP/s"
                    % (peak_tf / 6.0, ef_tflops / (peak_tf / 6.0), sm_mhz, fp32_peak_tf))
     else:

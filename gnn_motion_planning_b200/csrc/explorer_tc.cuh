@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(HALVES == 1 ? 384 : (RD ? 576 : 544), 1) edge_
       const uint32_t img_s = smem_u32(img), tab_s = smem_u32(tabbuf);
       const uint32_t tc = tm_u + (uint32_t)t * 256u, xh = tc + Cf::cXH, xl = tc + Cf::cXL;
       auto wd = [&](int off, int rows) { return umma::desc_lo32(img_s + (uint32_t)off * 4u, (uint32_t)rows); };
-      auto raw_meta = [&](int u) { return u < n_units ? __ldg(unit_meta + u) : make_int4(0, 0, 0, 0); };
+      auto raw_meta = [&](int u) { return __ldg(unit_meta + min(u, n_units - 1)); };   // clamped: no select waiting on the load
       auto load_table = [&](const int4 mm_raw, int blk) {          // table of (unit with metadata mm_raw, Block blk) -> tabbuf
         const int O = __shfl_sync(0xffffffffu, mm_raw.z, 0), off = __shfl_sync(0xffffffffu, mm_raw.w, 0);
         const int nch = tc_nchunks(O), per = tc_per(O, nch);
@@ -326,13 +326,9 @@ __global__ void __launch_bounds__(HALVES == 1 ? 384 : (RD ? 576 : 544), 1) edge_
     const uint32_t img_s = smem_u32(img), tab_s = smem_u32(tabbuf);
     uint32_t rph[2] = {0, 0}, full_ph = 0;
     // unit metadata, one unit ahead of its use (uniform: every lane loads the same 16 bytes)
-    auto load_meta = [&](int u) {
-      int4 mm = make_int4(0, 0, 0, 0);
-      if (u < n_units) mm = __ldg(unit_meta + u);
-      mm.z = __shfl_sync(0xffffffffu, mm.z, 0);
-      mm.w = __shfl_sync(0xffffffffu, mm.w, 0);
-      return mm;
-    };
+    // (raw, index clamped: the broadcast that makes the fields provably uniform happens where they are consumed, a unit later,
+    //  so the issuer never waits on the load itself)
+    auto load_meta = [&](int u) { return __ldg(unit_meta + min(u, n_units - 1)); };
     int4 meta_cur = load_meta(blockIdx.x), meta_next = load_meta(blockIdx.x + gridDim.x);
     int cur_unit = blockIdx.x;
     // table cursor: next (unit, blk, pair of sub-chunks) to load.  tab_busy: the buffer holds (or is receiving) a table
@@ -343,11 +339,11 @@ __global__ void __launch_bounds__(HALVES == 1 ? 384 : (RD ? 576 : 544), 1) edge_
       if (tab_busy) return;
       while (cu_unit < n_units) {
         const int4 mm = cu_unit == cur_unit ? meta_cur : (cu_unit == cur_unit + (int)gridDim.x ? meta_next : load_meta(cu_unit));
-        const int O = mm.z;
+        const int O = __shfl_sync(0xffffffffu, mm.z, 0), tab_off = __shfl_sync(0xffffffffu, mm.w, 0);
         const int nch = tc_nchunks(O), per = tc_per(O, nch);
         if (n_blocks == 0 || nch == 0) { cu_unit += gridDim.x; continue; }
         const int ns = min(2, nch - 2 * cu_s);
-        const float* src = tc_tables + (size_t)cu_blk * tc_tab_stride + (size_t)mm.w + (size_t)(2 * cu_s) * (4 * E * per);
+        const float* src = tc_tables + (size_t)cu_blk * tc_tab_stride + (size_t)tab_off + (size_t)(2 * cu_s) * (4 * E * per);
         const uint32_t bytes = (uint32_t)(ns * 4 * E * per) * 4u;
         if (umma::elect_one()) {
           mbar_expect_tx(&bar_tabfull, bytes);
@@ -372,7 +368,7 @@ __global__ void __launch_bounds__(HALVES == 1 ? 384 : (RD ? 576 : 544), 1) edge_
         meta_cur = meta_next;
         meta_next = load_meta(unit + gridDim.x);
       }
-      const int O = meta_cur.z;
+      const int O = __shfl_sync(0xffffffffu, meta_cur.z, 0);
       const int nch = n_blocks ? tc_nchunks(O) : 0, per = tc_per(O, nch);
       // one stage for both tiles: wait for the tile's operands, issue, commit.  Exactly ONE commit per `ready` phase: a
       // `done` phase must be observed by all 128 waiters before the next one can complete (mbarrier waits are by parity; a
@@ -522,7 +518,9 @@ __global__ void __launch_bounds__(HALVES == 1 ? 384 : (RD ? 576 : 544), 1) edge_
     };
     // two units of metadata and one unit of endpoints are kept in flight, so that no load of the chain
     // meta -> CSR endpoints -> node coordinates ever waits on the one before it
-    auto load_meta = [&](int u) { return u < n_units ? __ldg(unit_meta + u) : make_int4(0, 0, 0, 0); };
+    // (index clamped instead of a select on the loaded value: a select would wait ~700 cycles for a load whose result is
+    //  needed two units later; the metadata of a unit past the end is never used -- the unit loop ends first)
+    auto load_meta = [&](int u) { return __ldg(unit_meta + min(u, n_units - 1)); };
     int4 meta_nx = load_meta(blockIdx.x), meta_nx2 = load_meta(blockIdx.x + gridDim.x);
     int s_nx = 0, d_nx = 0;
     auto load_endpoints = [&](const int4 mm) {
@@ -731,14 +729,16 @@ __global__ void __launch_bounds__(HALVES == 1 ? 384 : (RD ? 576 : 544), 1) edge_
       tc_detail::ld_cols<E>(tc + Cf::cA1 + 32, x);
       umma::wait_ld();
       if (valid) {
-        float4* q4 = reinterpret_cast<float4*>(Q + (size_t)slot * E);
-        float4* p4 = reinterpret_cast<float4*>(P + (size_t)slot * E);
+        float* qr = Q + (size_t)slot * E;
+        float* pr = P + (size_t)slot * E;
+        const float* qb = vec + Cf::vQb;
+        const float* pb = vec + Cf::vPb;
 #pragma unroll
-        for (int n = 0; n < E; n += 4) {
-          q4[n >> 2] = make_float4(q[n] + vec[Cf::vQb + n], q[n + 1] + vec[Cf::vQb + n + 1], q[n + 2] + vec[Cf::vQb + n + 2],
-                                   q[n + 3] + vec[Cf::vQb + n + 3]);
-          p4[n >> 2] = make_float4(x[n] + vec[Cf::vPb + n], x[n + 1] + vec[Cf::vPb + n + 1], x[n + 2] + vec[Cf::vPb + n + 2],
-                                   x[n + 3] + vec[Cf::vPb + n + 3]);
+        for (int n = 0; n < E; n += 8) {
+          umma::st_global_v8(qr + n, q[n] + qb[n], q[n + 1] + qb[n + 1], q[n + 2] + qb[n + 2], q[n + 3] + qb[n + 3], q[n + 4] + qb[n + 4],
+                             q[n + 5] + qb[n + 5], q[n + 6] + qb[n + 6], q[n + 7] + qb[n + 7]);
+          umma::st_global_v8(pr + n, x[n] + pb[n], x[n + 1] + pb[n + 1], x[n + 2] + pb[n + 2], x[n + 3] + pb[n + 3], x[n + 4] + pb[n + 4],
+                             x[n + 5] + pb[n + 5], x[n + 6] + pb[n + 6], x[n + 7] + pb[n + 7]);
         }
       }
     }
@@ -827,7 +827,9 @@ __global__ void __launch_bounds__(HALVES == 1 ? 384 : (RD ? 576 : 544), 1) edge_
 #ifdef GMP_TC_PROFILE
     prof_xp = &prof_x;
 #endif
-    auto load_meta = [&](int u) { return u < n_units ? __ldg(unit_meta + u) : make_int4(0, 0, 0, 0); };
+    // (index clamped instead of a select on the loaded value: a select would wait ~700 cycles for a load whose result is
+    //  needed two units later; the metadata of a unit past the end is never used -- the unit loop ends first)
+    auto load_meta = [&](int u) { return __ldg(unit_meta + min(u, n_units - 1)); };
     int4 meta_nx = load_meta(blockIdx.x), meta_nx2 = load_meta(blockIdx.x + gridDim.x);
     int s_nx = 0, d_nx = 0;
     auto load_endpoints = [&](const int4 mm) {
@@ -1047,14 +1049,16 @@ __global__ void __launch_bounds__(HALVES == 1 ? 384 : (RD ? 576 : 544), 1) edge_
       umma::ld16(tc + Cf::cA1 + 32 + c0, x);
       umma::wait_ld();
       if (valid) {
-        float4* q4 = reinterpret_cast<float4*>(Q + (size_t)slot * E + c0);
-        float4* p4 = reinterpret_cast<float4*>(P + (size_t)slot * E + c0);
+        float* qr = Q + (size_t)slot * E + c0;
+        float* pr = P + (size_t)slot * E + c0;
+        const float* qb = vec + Cf::vQb + c0;
+        const float* pb = vec + Cf::vPb + c0;
 #pragma unroll
-        for (int n = 0; n < H; n += 4) {
-          q4[n >> 2] = make_float4(q[n] + vec[Cf::vQb + c0 + n], q[n + 1] + vec[Cf::vQb + c0 + n + 1], q[n + 2] + vec[Cf::vQb + c0 + n + 2],
-                                   q[n + 3] + vec[Cf::vQb + c0 + n + 3]);
-          p4[n >> 2] = make_float4(x[n] + vec[Cf::vPb + c0 + n], x[n + 1] + vec[Cf::vPb + c0 + n + 1], x[n + 2] + vec[Cf::vPb + c0 + n + 2],
-                                   x[n + 3] + vec[Cf::vPb + c0 + n + 3]);
+        for (int n = 0; n < H; n += 8) {
+          umma::st_global_v8(qr + n, q[n] + qb[n], q[n + 1] + qb[n + 1], q[n + 2] + qb[n + 2], q[n + 3] + qb[n + 3], q[n + 4] + qb[n + 4],
+                             q[n + 5] + qb[n + 5], q[n + 6] + qb[n + 6], q[n + 7] + qb[n + 7]);
+          umma::st_global_v8(pr + n, x[n] + pb[n], x[n + 1] + pb[n + 1], x[n + 2] + pb[n + 2], x[n + 3] + pb[n + 3], x[n + 4] + pb[n + 4],
+                             x[n + 5] + pb[n + 5], x[n + 6] + pb[n + 6], x[n + 7] + pb[n + 7]);
         }
       }
     }

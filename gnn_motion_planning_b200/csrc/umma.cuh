@@ -161,6 +161,13 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// one 256-bit global store (sm_100: STG.256): the lane writes a whole 32-byte sector, so a row-per-lane store pattern costs half
+// the store instructions and no partial-sector writes
+__device__ __forceinline__ void st_global_v8(float* p, float a0, float a1, float a2, float a3, float a4, float a5, float a6, float a7) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(a0), "f"(a1), "f"(a2), "f"(a3), "f"(a4), "f"(a5), "f"(a6),
+               "f"(a7) : "memory");
+}
+
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }

@@ -146,7 +146,7 @@ __device__ __forceinline__ void layernorm_row(float* x, const float* __restrict_
     v0 = fmaf(d0, d0, v0); v1 = fmaf(d1, d1, v1); v2 = fmaf(d2, d2, v2); v3 = fmaf(d3, d3, v3);
   }
   const float var = ((v0 + v1) + (v2 + v3)) * (1.0f / N);
-  const float rstd = 1.0f / sqrtf(var + eps);
+  const float rstd = rsqrtf(var + eps);   // one MUFU (2 ulp) instead of the ~20-instruction IEEE sqrt + divide; tolerance 1e-4 on the logits
 #pragma unroll
   for (int n = 0; n < N; ++n) x[n] = (x[n] - mu) * rstd * gamma[n] + beta[n];
 }
@@ -820,7 +820,7 @@ __global__ void __launch_bounds__(HALVES == 1 ? 384 : (RD ? 576 : 544), 1) edge_
         v0 = fmaf(d0, d0, v0); v1 = fmaf(d1, d1, v1); v2 = fmaf(d2, d2, v2); v3 = fmaf(d3, d3, v3);
       }
       const float var = xsum((v0 + v1) + (v2 + v3)) * (1.0f / E);
-      const float rstd = 1.0f / sqrtf(var + 1e-6f);
+      const float rstd = rsqrtf(var + 1e-6f);
 #pragma unroll
       for (int n = 0; n < H; ++n) y[n] = (y[n] - mu) * rstd * gamma[c0 + n] + beta[c0 + n];
     };

@@ -832,13 +832,25 @@ __global__ void __launch_bounds__(HALVES == 1 ? 384 : (RD ? 576 : 544), 1) edge_
     auto load_meta = [&](int u) { return __ldg(unit_meta + min(u, n_units - 1)); };
     int4 meta_nx = load_meta(blockIdx.x), meta_nx2 = load_meta(blockIdx.x + gridDim.x);
     int s_nx = 0, d_nx = 0;
-    auto load_endpoints = [&](const int4 mm) {
-      const int sl = mm.x + tile * 128 + row;
-      const bool ok = sl < mm.y;
-      s_nx = ok ? __ldg(csr_src + sl) : 0;
-      d_nx = ok ? __ldg(csr_dst + sl) : 0;
+    auto load_endpoints = [&](const int4 mm) {   // (slot clamped into the graph instead of a select on the loaded ids; rows past the end are never stored)
+      const int sl = min(mm.x + tile * 128 + row, mm.y - 1);
+      s_nx = __ldg(csr_src + sl);
+      d_nx = __ldg(csr_dst + sl);
     };
     load_endpoints(meta_nx);
+    // narrow inputs: the endpoints' coordinates of the NEXT unit are requested before the tail of the current one, so that the
+    // unit starts with its inputs in registers instead of a dependent gather (ids -> coordinates, ~2 L2 latencies)
+    float in_nx[Cf::kSimtIn ? 2 * C : 1];
+    auto gather_next = [&]() {
+      if constexpr (Cf::kSimtIn) {
+#pragma unroll
+        for (int k = 0; k < C; ++k) {
+          in_nx[k] = __ldg(v + (size_t)s_nx * C + k);
+          in_nx[C + k] = __ldg(v + (size_t)d_nx * C + k);
+        }
+      }
+    };
+    gather_next();
     for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
       const int4 meta = meta_nx;
       const int slot = meta.x + tile * 128 + row;
@@ -888,10 +900,12 @@ __global__ void __launch_bounds__(HALVES == 1 ? 384 : (RD ? 576 : 544), 1) edge_
       // ---- edge_free_code                                                  (model.py:123)
       {
         float in[K0];
-        gather(in);
         if constexpr (Cf::kSimtIn) {
+#pragma unroll
+          for (int k = 0; k < K0; ++k) in[k] = k < 2 * C ? in_nx[k] : 0.f;   // requested before the previous unit's tail
           simt_hidden(in, 0, x);
         } else {
+          gather(in);
           umma::st_split<K0 / 2>(tc + Cf::cXH + half * (K0 / 2), tc + Cf::cXL + half * (K0 / 2), in + half * (K0 / 2));
           publish();
           await();
@@ -1043,6 +1057,7 @@ __global__ void __launch_bounds__(HALVES == 1 ? 384 : (RD ? 576 : 544), 1) edge_
         publish();
       }
       // ---- Q = Wc ef + b (model.py:145-146);  P = W4 ef + W5 edge_code + b (model.py:39), edge_code.2 folded into W5
+      gather_next();   // (the next unit's endpoint ids landed a unit ago)
       await(4);
       float q[H];
       umma::ld16(tc + Cf::cA1 + c0, q);

@@ -1274,10 +1274,11 @@ __global__ void __launch_bounds__(128, MsgTc<E_>::kCtas) edge_msg_tc_kernel(cons
       float mrow[E];
       tc_detail::ld_cols<E>(trow + M::cD, mrow);
       umma::wait_ld();
+      // (no bias here: x -> fl(x + b) is monotone, so max_i fl(m_i + b) == fl(max_i m_i + b) bit for bit -- the bias is added
+      //  once per (segment, feature) when the maximum is flushed instead of once per (row, feature))
 #pragma unroll
       for (int n = 0; n < E; n += 4)
-        *reinterpret_cast<float4*>(X + threadIdx.x * XP + n) =
-            make_float4(mrow[n] + bias[n], mrow[n + 1] + bias[n + 1], mrow[n + 2] + bias[n + 2], mrow[n + 3] + bias[n + 3]);
+        *reinterpret_cast<float4*>(X + threadIdx.x * XP + n) = make_float4(mrow[n], mrow[n + 1], mrow[n + 2], mrow[n + 3]);
     }
     umma::fence_before_sync();
     __syncthreads();
@@ -1292,22 +1293,27 @@ __global__ void __launch_bounds__(128, MsgTc<E_>::kCtas) edge_msg_tc_kernel(cons
     const int lane = threadIdx.x & 31;
     int cur = -1;
     float run = -INFINITY;
+    const float bn = bias[n];
 #pragma unroll
     for (int c = 0; c < ROWS / 32; ++c) {
       const int dl = IDX[r0 + 32 * c + lane];
       int prev = __shfl_up_sync(0xffffffffu, dl, 1);
       if (lane == 0) prev = cur;   // (cur is warp-uniform: the target of the previous chunk's last row, -1 at the start)
       const uint32_t heads = __ballot_sync(0xffffffffu, dl != prev);
+      float xv[32];                // the column slice first (32 independent loads), then the dependent max chain
+#pragma unroll
+      for (int i = 0; i < 32; ++i) xv[i] = X[(r0 + 32 * c + i) * XP + n];
+#pragma unroll
       for (int i = 0; i < 32; ++i) {
         if ((heads >> i) & 1u) {
-          if (cur >= 0) atomic_max_f32(AGG + (size_t)cur * E + n, run);
+          if (cur >= 0) atomic_max_f32(AGG + (size_t)cur * E + n, run + bn);
           cur = __shfl_sync(0xffffffffu, dl, i);
           run = -INFINITY;
         }
-        run = fmaxf(run, X[(r0 + 32 * c + i) * XP + n]);
+        run = fmaxf(run, xv[i]);
       }
     }
-    if (cur >= 0) atomic_max_f32(AGG + (size_t)cur * E + n, run);
+    if (cur >= 0) atomic_max_f32(AGG + (size_t)cur * E + n, run + bn);
     // (the loop-top barrier protects X, the parity buffers protect IDX; tensor memory is rewritten only after the next tile's barriers)
   }
   umma::fence_before_sync();

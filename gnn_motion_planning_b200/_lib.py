@@ -73,6 +73,7 @@ SIGNATURES = {
                                      c_void_p, c_float, c_int, c_void_p, c_void_p, c_int64, c_void_p]),
     "gmp_result_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p]),
     "gmp_edge_index_narrow": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_int64, c_void_p]),
+    "gmp_post_to_host": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
 }
 
 _lib = None

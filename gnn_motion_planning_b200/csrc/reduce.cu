@@ -51,10 +51,28 @@ __global__ void __launch_bounds__(256) narrow_ids_kernel(const int64_t* __restri
   }
 }
 
+// a few words device -> MAPPED pinned host memory with plain stores (posted PCIe writes): unlike cudaMemcpyAsync it does not queue
+// on the device->host copy engine behind a large read-back that is still in flight
+__global__ void __launch_bounds__(256) post_words_kernel(const uint32_t* __restrict__ src, int64_t n, volatile uint32_t* dst_host) {
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) dst_host[i] = src[i];
+  __threadfence_system();
+}
+
 }  // namespace
 }  // namespace gmp
 
 using namespace gmp;
+
+extern "C" int gmp_post_to_host(const void* src_device, int64_t nbytes, void* dst_mapped_host, void* stream) {
+  GMP_REQUIRE(nbytes >= 0 && nbytes % 4 == 0 && nbytes <= (1 << 20), "nbytes must be a multiple of 4, at most 1 MiB (small control data only)");
+  if (nbytes == 0) return GMP_OK;
+  GMP_REQUIRE(src_device && dst_mapped_host, "null pointer");
+  const int64_t n = nbytes / 4;
+  post_words_kernel<<<(int)std::min<int64_t>((n + 255) / 256, 64), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint32_t*>(src_device), n, static_cast<volatile uint32_t*>(dst_mapped_host));
+  GMP_LAUNCH_CHECK();
+  return GMP_OK;
+}
 
 extern "C" int gmp_edge_index_narrow(const int64_t* edge_index, int64_t edge_row_stride, int64_t n_edges, int bits,
                                      void* out, int64_t out_row_stride, void* stream) {

@@ -27,11 +27,14 @@ def _workspace(device, nbytes):
 
 
 @torch.no_grad()
-def knn_graph_batch(v, node_ptr, n_free, k1, edge_index_out=None):
+def knn_graph_batch(v, node_ptr, n_free, k1, edge_index_out=None, edge_ptr_host=None):
     """Symmetrised, coalesced k-NN graphs of a packed batch.
 
     v [N_total,c] f32 cuda; node_ptr [B+1], n_free [B], k1 [B] host ints.
     Returns (edge_index [2, capacity] i64 cuda -- valid columns are [0, edge_ptr[-1]) --, edge_ptr [B+1] host int32).
+    edge_ptr_host: optional PINNED int32 [B+1] tensor; edge_ptr is then written into it by a kernel (``gmp_post_to_host``)
+    instead of a device->host copy, so that this -- the only host synchronisation of a batch -- does not queue behind a large
+    read-back in flight on the copy engine (pipelined callers: ``batch.HotPath``).
     """
     _lib.require_cuda(v, "v")
     lib = _lib.load()
@@ -56,7 +59,16 @@ def knn_graph_batch(v, node_ptr, n_free, k1, edge_index_out=None):
     _lib.check(lib.gmp_knn_graph(None, B, _lib.ptr(v), v.shape[1], _lib.ptr(node_ptr), _lib.ptr(n_free), _lib.ptr(k1),
                                  _lib.ptr(edge_index_out), edge_index_out.shape[1], _lib.ptr(edge_ptr), _lib.ptr(ws),
                                  ws.numel(), _lib.stream_ptr(dev)))
-    return edge_index_out, edge_ptr.cpu().numpy()
+    if edge_ptr_host is None:
+        return edge_index_out, edge_ptr.cpu().numpy()
+    if (not edge_ptr_host.is_pinned() or edge_ptr_host.dtype != torch.int32 or edge_ptr_host.numel() != B + 1
+            or not edge_ptr_host.is_contiguous()):
+        raise ValueError("edge_ptr_host must be a pinned contiguous int32 [B+1] tensor")
+    _lib.check(lib.gmp_post_to_host(_lib.ptr(edge_ptr), 4 * (B + 1), edge_ptr_host.data_ptr(), _lib.stream_ptr(dev)))
+    done = torch.cuda.Event()
+    done.record(torch.cuda.current_stream(dev))
+    done.synchronize()
+    return edge_index_out, edge_ptr_host.numpy().copy()
 
 
 @torch.no_grad()

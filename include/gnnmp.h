@@ -297,6 +297,12 @@ int gmp_result_rows(const float* edge_logits, const uint8_t* edge_free, const in
 int gmp_edge_index_narrow(const int64_t* edge_index, int64_t edge_row_stride, int64_t n_edges, int bits, void* out,
                           int64_t out_row_stride, void* stream);
 
+/* Small control data (<= 1 MiB, a multiple of 4 bytes) device -> pinned host memory that is mapped into the device's address
+ * space (cudaHostAlloc / torch pin_memory under UVA), written by a kernel instead of a copy engine: the per-batch edge_ptr
+ * [B+1] the host needs before it can enqueue the forward (eval_gnn.py:164 builds the graph on the host; here it is the one
+ * host synchronisation of a batch) must not wait behind the previous batch's 100 MB read-back on the same copy engine. */
+int gmp_post_to_host(const void* src_device, int64_t nbytes, void* dst_mapped_host, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -36,6 +36,12 @@ def test_batched_ragged_vs_oracle(cuda_device):
         node_ptr.append(node_ptr[-1] + n); nf.append(f); k1.append(k)
     v = np.concatenate(vs)
     ei, ep = graph.knn_graph_batch(torch.from_numpy(v).to(cuda_device), node_ptr, nf, k1)
+    # the same call with edge_ptr posted into pinned host memory by a kernel (gmp_post_to_host) instead of a copy-engine read-back
+    pin = torch.full((len(sizes) + 1,), -1, dtype=torch.int32).pin_memory()
+    ei2, ep2 = graph.knn_graph_batch(torch.from_numpy(v).to(cuda_device), node_ptr, nf, k1, edge_ptr_host=pin)
+    assert np.array_equal(ep, ep2) and np.array_equal(pin.numpy(), ep) and torch.equal(ei[:, :ep[-1]], ei2[:, :ep[-1]])
+    with pytest.raises(ValueError):
+        graph.knn_graph_batch(torch.from_numpy(v).to(cuda_device), node_ptr, nf, k1, edge_ptr_host=torch.zeros(len(sizes) + 1, dtype=torch.int32))
     ei = ei.cpu().numpy()
     for g, (n, f, k, _) in enumerate(sizes):
         want = o_knn.knn_graph_edges(vs[g], f, k)

@@ -15,8 +15,6 @@ across batches.  The edge list travels back as LOCAL ids in int16 (int32 when a 
 4 B/edge instead of the 16 B/edge of the int64 ``[2,E]`` PyG layout, which was 76 % of the read-back (the int64 tensor
 stays on the device for the kernels; ``result["edge_index"].to(torch.int64)`` restores the reference dtype on the host).
 """
-import os
-
 import numpy as np
 import torch
 
@@ -141,13 +139,10 @@ class HotPath:
         s["compute_done"].record(main)
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(s["compute_done"])
-            diag = os.environ.get("GMP_HOTPATH_DIAG", "")      # measurement only: which read-back the 8-GPU end-to-end rate pays for
-            if diag != "nocopy":
-                s["host"]["logits"][:n].copy_(s["logits"][:n], non_blocking=True)
-                s["host"]["free"][:n].copy_(s["free"][:n], non_blocking=True)
-                if diag != "noids":
-                    s["host"]["ei"][0, :n].copy_(s["ei_narrow"][0, :n], non_blocking=True)
-                    s["host"]["ei"][1, :n].copy_(s["ei_narrow"][1, :n], non_blocking=True)
+            s["host"]["logits"][:n].copy_(s["logits"][:n], non_blocking=True)
+            s["host"]["free"][:n].copy_(s["free"][:n], non_blocking=True)
+            s["host"]["ei"][0, :n].copy_(s["ei_narrow"][0, :n], non_blocking=True)
+            s["host"]["ei"][1, :n].copy_(s["ei_narrow"][1, :n], non_blocking=True)
             s["host"]["rows"].copy_(s["rows"], non_blocking=True)
             s["copy_done"].record(self.copy_stream)
         s["h2d_bytes"] = sum(t.numel() * t.element_size() for t in (v_h, goal_h, obs_h, prob_h) + ((maps_h,) if maps_h is not None else ()))

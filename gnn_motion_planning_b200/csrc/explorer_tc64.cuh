@@ -195,16 +195,14 @@ __global__ void __launch_bounds__(384, 1) edge_feature64_tc_kernel(
       dph ^= 1u;
       umma::fence_after_sync();
     };
+    // rows are 256 B per lane: 256-bit accesses (whole 32-byte sectors per lane, half the instructions of float4s)
     auto load_row = [&](const float* p, float* x) {   // 64 contiguous floats
 #pragma unroll
-      for (int n = 0; n < E; n += 4) {
-        const float4 t4 = *reinterpret_cast<const float4*>(p + n);
-        x[n] = t4.x; x[n + 1] = t4.y; x[n + 2] = t4.z; x[n + 3] = t4.w;
-      }
+      for (int n = 0; n < E; n += 8) umma::ld_global_v8(p + n, x + n);
     };
     auto store_row = [&](float* p, const float* x) {
 #pragma unroll
-      for (int n = 0; n < E; n += 4) *reinterpret_cast<float4*>(p + n) = make_float4(x[n], x[n + 1], x[n + 2], x[n + 3]);
+      for (int n = 0; n < E; n += 8) umma::st_global_v8(p + n, x[n], x[n + 1], x[n + 2], x[n + 3], x[n + 4], x[n + 5], x[n + 6], x[n + 7]);
     };
     int4 meta_nx = make_int4(0, 0, 0, 0);
     int s_nx = 0, d_nx = 0;

@@ -170,6 +170,12 @@ __device__ __forceinline__ void st_global_v8(float* p, float a0, float a1, float
                "f"(a7) : "memory");
 }
 
+// ... and the matching 256-bit load (LDG.256)
+__device__ __forceinline__ void ld_global_v8(const float* p, float* a) {
+  asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(a[0]), "=f"(a[1]), "=f"(a[2]), "=f"(a[3]), "=f"(a[4]), "=f"(a[5]), "=f"(a[6]), "=f"(a[7]) : "l"(p) : "memory");
+}
+
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }

@@ -153,21 +153,30 @@ __device__ __forceinline__ void acc_layernorm(float (&acc)[TM][N], const float* 
 }
 
 // row vector (N contiguous floats in global memory) -> this thread's column;  p == nullptr -> zeros
+// (rows are N * 4 B apart, N a multiple of 8, in 256-byte-aligned buffers: one 256-bit access per 8 floats -- whole 32-byte sectors
+//  per lane and half the LSU instructions of float4s in these row-per-thread patterns)
 template <int N, int RP>
 __device__ __forceinline__ void col_load_global(float* __restrict__ col1, const float* __restrict__ p) {
+  static_assert(N % 8 == 0, "N % 8");
 #pragma unroll
-  for (int n = 0; n < N; n += 4) {
-    float4 x = p ? __ldg(reinterpret_cast<const float4*>(p + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    col1[n * RP] = x.x; col1[(n + 1) * RP] = x.y; col1[(n + 2) * RP] = x.z; col1[(n + 3) * RP] = x.w;
+  for (int n = 0; n < N; n += 8) {
+    float x[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (p)
+      asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                   : "=f"(x[0]), "=f"(x[1]), "=f"(x[2]), "=f"(x[3]), "=f"(x[4]), "=f"(x[5]), "=f"(x[6]), "=f"(x[7]) : "l"(p + n));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) col1[(n + i) * RP] = x[i];
   }
 }
 
 // accumulators of sub-row r -> N contiguous floats in global memory
 template <int TM, int N>
 __device__ __forceinline__ void acc_store_global(const float (&acc)[TM][N], int r, float* __restrict__ p) {
+  static_assert(N % 8 == 0, "N % 8");
 #pragma unroll
-  for (int n = 0; n < N; n += 4)
-    *reinterpret_cast<float4*>(p + n) = make_float4(acc[r][n], acc[r][n + 1], acc[r][n + 2], acc[r][n + 3]);
+  for (int n = 0; n < N; n += 8)
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p + n), "f"(acc[r][n]), "f"(acc[r][n + 1]), "f"(acc[r][n + 2]),
+                 "f"(acc[r][n + 3]), "f"(acc[r][n + 4]), "f"(acc[r][n + 5]), "f"(acc[r][n + 6]), "f"(acc[r][n + 7]) : "memory");
 }
 
 __device__ __forceinline__ int find_segment(const int32_t* __restrict__ ptr, int n_seg, int x) {

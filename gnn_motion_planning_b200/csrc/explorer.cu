@@ -1627,7 +1627,7 @@ extern "C" int gmp_explorer_bad_edges(gmp_handle* h, void* stream) {
 
 extern "C" int gmp_explorer_set_edge_feature_mode(gmp_handle* h, int mode) {
   GMP_REQUIRE(h, "null handle");
-  GMP_REQUIRE(mode >= -1 && mode <= 3, "mode: -1 auto, 0 fp32 SIMT, 1 tcgen05 3xTF32, 2 tcgen05 with the round-1 four-warp tiles, 3 tcgen05 with the ready-driven issuer");
+  GMP_REQUIRE(mode >= -1 && mode <= 3, "mode: -1 auto, 0 fp32 SIMT, 1 tcgen05 3xTF32, 2 tcgen05 with the round-1 four-warp tiles, 3 tcgen05 with one issuer warp per tile");
   h->ex.edge_feature_mode = mode;
   return GMP_OK;
 }

@@ -48,7 +48,9 @@ struct ExplorerW {
 struct ExplorerModel {
   int c = 0, e = 0, s = 0;
   bool ready = false;
-  int edge_feature_mode = -1;        // -1 auto (tensor cores when e == 32), 0 fp32 SIMT, 1 tcgen05 3xTF32
+  // -1 auto, 0 fp32 SIMT, 1 tcgen05 3xTF32 with eight epilogue warps per tile and one lockstep issuer, 2 the same with four warps
+  // per tile, 3 eight warps per tile and one issuer warp per tile (what auto runs for narrow inputs with 1..128 obstacles)
+  int edge_feature_mode = -1;
   std::map<std::string, std::vector<float>> tensors;  // reference state_dict (live entries)
   ExplorerW w{};
   float* d_weights = nullptr;

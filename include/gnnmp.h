@@ -62,8 +62,11 @@ int gmp_explorer_finalize(gmp_handle* h);
 /* Arithmetic of the edge-feature stage (edge encoders + edge Blocks, model.py:120,123,130):
  *   -1 auto (default) / 1: tcgen05 tensor cores with 3xTF32 split operands (embed_size 64: graphs with more than 32
  *    obstacles fall back to fp32 FMA for the edge-feature stage);  0: fp32 FMA (SIMT) always;  2: tensor cores with the
- *    round-1 tile organisation of the embed-32 kernel (four epilogue warps per tile instead of eight).
- * Both meet the 1e-4 logit tolerance; the switch exists for A/B parity tests and profiling. */
+ *    round-1 tile organisation of the embed-32 kernel (four epilogue warps per tile instead of eight);  3: eight warps per
+ *    tile and one MMA issuer warp per tile instead of one for both (what auto runs for narrow inputs, 2c <= 8, when every
+ *    graph has 1..128 obstacles; bit-identical to mode 1).  The environment variable GMP_TC_RD=0 / 1 overrides the issuer
+ *    choice for A/B measurements.
+ * All meet the 1e-4 logit tolerance; the switch exists for A/B parity tests and profiling. */
 int gmp_explorer_set_edge_feature_mode(gmp_handle* h, int mode);
 
 /* Bytes of scratch gmp_explorer_forward needs for a batch of these totals. */

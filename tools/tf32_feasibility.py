@@ -1,6 +1,7 @@
 """CPU experiment: would a 3xTF32 (hi/lo split) tensor-core formulation of the explorer's dense layers stay inside the
 1e-4 logit gate?  Emulates every Linear / attention product with operands rounded to TF32 (10 explicit mantissa bits)
-and fp32 accumulation, in three variants: 1xTF32, 3xTF32 (hi*hi + hi*lo + lo*hi), and plain fp32, each compared with the
+and fp32 accumulation, in four variants: 1xTF32, 3xTF32 (hi*hi + hi*lo + lo*hi), 2xTF32 on the weight products (the
+weights' lo plane dropped), and plain fp32, each compared with the
 fp64 evaluation of the same graph.   python tools/tf32_feasibility.py"""
 import os
 import sys
@@ -22,18 +23,20 @@ def tf32(x):
     return r.view(torch.float32)
 
 
-def mm(a, b):
+def mm(a, b, b_is_weight=False):
     if a.dtype != torch.float32 or MODE["m"] == "fp32":
         return a @ b
     ah, bh = tf32(a), tf32(b)
     if MODE["m"] == "tf32x1":
         return ah @ bh
     al, bl = tf32(a - ah), tf32(b - bh)
+    if MODE["m"] == "tf32x2w" and b_is_weight:   # drop A_hi . B_lo where B is a weight plane (two MMAs per product)
+        return al @ bh + ah @ bh
     return (al @ bh + ah @ bl) + ah @ bh      # small terms first
 
 
 def _lin(x, sd, name, bias=True):
-    y = mm(x, sd[name + ".weight"].t())
+    y = mm(x, sd[name + ".weight"].t(), b_is_weight=True)
     return y + sd[name + ".bias"] if bias else y
 
 
@@ -61,7 +64,7 @@ for g in range(2):
     obs = torch.from_numpy((np.argwhere(maps[g] == 1) / 15.0 - 0.5).astype(np.float32))
     MODE["m"] = "fp32"
     f64 = ox.explorer_forward(sd, vt, ei, vt[1], obs, loop=5, dense=False, dtype=torch.float64)
-    for mode in ("fp32", "tf32x3", "tf32x1"):
+    for mode in ("fp32", "tf32x3", "tf32x2w", "tf32x1"):
         MODE["m"] = mode
         got = ox.explorer_forward(sd, vt, ei, vt[1], obs, loop=5, dense=False).double()
         print("graph %d  %-7s max|logit - fp64| = %.3e   (|logit|max %.1f)" % (g, mode, float((got - f64).abs().max()), float(f64.abs().max())))

@@ -45,5 +45,8 @@ extern "C" void gmp_destroy(gmp_handle* h) {
   cudaSetDevice(h->device);
   if (h->ex.d_weights) cudaFree(h->ex.d_weights);
   if (h->sm.d_weights) cudaFree(h->sm.d_weights);
+  if (h->ex_side) cudaStreamDestroy(h->ex_side);
+  if (h->ex_fork) cudaEventDestroy(h->ex_fork);
+  if (h->ex_join) cudaEventDestroy(h->ex_join);
   delete h;
 }

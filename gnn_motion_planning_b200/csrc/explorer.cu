@@ -1404,24 +1404,38 @@ int run_forward(gmp_handle* h, int64_t B, const float* v, const int64_t* edge_in
 
   Timeline& tl = h->tl;
   tl.reset();
-  // CSR by target
-  tl.begin(kPhCsr, st);
-  if (Nt > 0) GMP_CUDA(cudaMemsetAsync(ws.indeg, 0, (Nt + 1) * sizeof(int32_t), st));
+  // CSR by target -- on the handle's side stream, forked here and joined before the first consumer of the CSR (the edge-feature
+  // stage): its 2 x E atomics are bound by L2 latency and overlap the node-side kernels below, which run at ~12 % occupancy
+  if (!h->ex_side) {
+    GMP_CUDA(cudaStreamCreateWithFlags(&h->ex_side, cudaStreamNonBlocking));
+    GMP_CUDA(cudaEventCreateWithFlags(&h->ex_fork, cudaEventDisableTiming));
+    GMP_CUDA(cudaEventCreateWithFlags(&h->ex_join, cudaEventDisableTiming));
+  }
+  const bool fork = getenv("GMP_NO_FORK") == nullptr;
+  cudaStream_t cs = fork ? h->ex_side : st;
+  if (fork) {
+    GMP_CUDA(cudaEventRecord(h->ex_fork, st));
+    GMP_CUDA(cudaStreamWaitEvent(cs, h->ex_fork, 0));
+  }
+  tl.begin(kPhCsr, cs);
+  if (Nt > 0) GMP_CUDA(cudaMemsetAsync(ws.indeg, 0, (Nt + 1) * sizeof(int32_t), cs));
+  const int csr_ctas = kNumSMs * (fork ? 8 : 16);           // forked: leave half of each SM's thread slots to the other stream
   if (Et > 0) {
-    int gx = (int)std::min<int64_t>((Et + 255) / 256, kNumSMs * 16);
-    csr_count_kernel<<<gx, 256, 0, st>>>(edge_index, row_stride, ws.edge_ptr, ws.node_ptr, (int)B, (int)Et, ws.indeg, ws.indeg + Nt);
+    int gx = (int)std::min<int64_t>((Et + 255) / 256, csr_ctas);
+    csr_count_kernel<<<gx, 256, 0, cs>>>(edge_index, row_stride, ws.edge_ptr, ws.node_ptr, (int)B, (int)Et, ws.indeg, ws.indeg + Nt);
     h->ex_bad_edges = ws.indeg + Nt;
     GMP_LAUNCH_CHECK();
   }
-  csr_scan_kernel<<<(int)B, 256, 0, st>>>(ws.indeg, ws.node_ptr, ws.edge_ptr, ws.in_ptr, ws.cursor);
+  csr_scan_kernel<<<(int)B, 256, 0, cs>>>(ws.indeg, ws.node_ptr, ws.edge_ptr, ws.in_ptr, ws.cursor);
   GMP_LAUNCH_CHECK();
   if (Et > 0) {
-    int gx = (int)std::min<int64_t>((Et + 255) / 256, kNumSMs * 16);
-    csr_fill_kernel<<<gx, 256, 0, st>>>(edge_index, row_stride, ws.edge_ptr, ws.node_ptr, (int)B, (int)Et, ws.in_ptr, ws.cursor,
+    int gx = (int)std::min<int64_t>((Et + 255) / 256, csr_ctas);
+    csr_fill_kernel<<<gx, 256, 0, cs>>>(edge_index, row_stride, ws.edge_ptr, ws.node_ptr, (int)B, (int)Et, ws.in_ptr, ws.cursor,
                                         ws.csr_src, ws.csr_dst, ws.csr_eid);
     GMP_LAUNCH_CHECK();
   }
-  tl.end(st);
+  tl.end(cs);
+  if (fork) GMP_CUDA(cudaEventRecord(h->ex_join, cs));
   tl.begin(kPhGoal, st);
   goal_index_kernel<<<(int)B, 256, 0, st>>>(v, goal, C, ws.node_ptr, ws.goal_idx);
   GMP_LAUNCH_CHECK();
@@ -1442,6 +1456,7 @@ int run_forward(gmp_handle* h, int64_t B, const float* v, const int64_t* edge_in
     GMP_LAUNCH_CHECK();
   }
   tl.end(st);
+  if (fork) GMP_CUDA(cudaStreamWaitEvent(st, h->ex_join, 0));   // join: everything below reads the CSR
   tl.begin(kPhEdgeFeature, st);
   bool tc_done = false;
   if constexpr (E == 32) {

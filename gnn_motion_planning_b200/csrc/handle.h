@@ -117,5 +117,9 @@ struct gmp_handle {
   // launch state of the explorer kernels on THIS handle's device (shared-memory opt-in done, persistent grid size)
   bool ex_attr_done = false;
   int ex_msg_grid = 0;
+  // fork / join of the explorer forward: the CSR build (bound by L2 atomic latency) runs on this side stream next to the
+  // node-side kernels (low occupancy) of the launching stream and is joined before the first kernel that reads the CSR
+  cudaStream_t ex_side = nullptr;
+  cudaEvent_t ex_fork = nullptr, ex_join = nullptr;
   const int32_t* ex_bad_edges = nullptr;   // device counter (in the caller's workspace) of out-of-range edge ids in the last forward
 };

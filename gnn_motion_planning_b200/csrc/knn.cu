@@ -26,6 +26,8 @@
 // (16 B per edge, int64 pairs) plus N*c*4 B in.  See DESIGN.md.
 #include <cstdlib>
 
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace gmp {
@@ -233,7 +235,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, NPL <= 32 ? 4 : 2) knn_sele
   const int k = min(k1s[g], cnt);
   const int wpr = (n + 31) >> 5;
   uint32_t* bm = bitmap + bm_ptr[g];
-  constexpr int L = 19;                                    // bits resolved on the compacted bucket
+  constexpr int L = 16;                                    // bits resolved on the compacted bucket
   for (int i = i_lo + warp; i < i_hi; i += kWarpsPerCta) {
     uint32_t d[NPL];
 #pragma unroll
@@ -263,10 +265,32 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, NPL <= 32 ? 4 : 2) knn_sele
         return __reduce_add_sync(0xffffffffu, (c0 + c1) + (c2 + c3));
       };
       int n_below = 0;                                     // count(d < T) for the current T
+      // first level on the top 16 bits only, two candidates per instruction: a non-negative float's upper half IS its
+      // truncated bfloat16, the candidate thresholds of this level have a zero lower half (d < cand  <=>  hi(d) < hi(cand)), so
+      // one HSET2.BF16 compares two packed distances and one HADD2.BF16 counts them (counts <= NPL, exact in bfloat16).  The
+      // padding word 0xffff is a NaN: never below anything, like 0xffffffff in the integer compare.  hi(cand) never reaches the
+      // inf / NaN patterns: a candidate with all exponent bits set would have to satisfy count(d < inf) < k with k < cnt.
+      uint32_t dp[NPL / 2];
+#pragma unroll
+      for (int t = 0; t < NPL / 2; ++t) dp[t] = __byte_perm(d[2 * t], d[2 * t + 1], 0x7632);
+      auto count_below16 = [&](uint32_t cand) {
+        const uint32_t c16 = cand >> 16, cc = c16 | (c16 << 16);
+        const __nv_bfloat162 c2 = *reinterpret_cast<const __nv_bfloat162*>(&cc);
+        __nv_bfloat162 a0 = __float2bfloat162_rn(0.0f), a1 = a0, a2 = a0, a3 = a0;
+#pragma unroll
+        for (int t = 0; t < NPL / 2; t += 4) {
+          a0 = __hadd2(a0, __hlt2(*reinterpret_cast<const __nv_bfloat162*>(&dp[t]), c2));
+          a1 = __hadd2(a1, __hlt2(*reinterpret_cast<const __nv_bfloat162*>(&dp[t + 1]), c2));
+          a2 = __hadd2(a2, __hlt2(*reinterpret_cast<const __nv_bfloat162*>(&dp[t + 2]), c2));
+          a3 = __hadd2(a3, __hlt2(*reinterpret_cast<const __nv_bfloat162*>(&dp[t + 3]), c2));
+        }
+        const __nv_bfloat162 a = __hadd2(__hadd2(a0, a1), __hadd2(a2, a3));
+        return __reduce_add_sync(0xffffffffu, (int)(__low2float(a) + __high2float(a)));
+      };
 #pragma unroll 1
       for (int bit = 30; bit >= L; --bit) {
         const uint32_t cand = T | (1u << bit);
-        const int cl = count_below(cand);
+        const int cl = count_below16(cand);
         if (cl < k) { T = cand; n_below = cl; }
       }
       // bucket: candidates with the threshold's top bits -> one register per lane
